@@ -1,0 +1,152 @@
+/*
+ * b200ret.h — C ABI of the B200-native first-stage retrieval engine.
+ *
+ * The reference (HansiZeng/scaling-retriever) is pure Python: its retrieval hot path calls numba,
+ * numpy and faiss-cpu directly and has no FFI of its own.  This header is the seam a maintainer binds
+ * (ctypes) underneath the reference's Python classes; every entry point names the
+ * reference interface it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless the parameter name ends in `_host`.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are asynchronous
+ *     with respect to the host unless stated otherwise.
+ *   - Every function returns 0 on success, a negative B200RET_E* code on failure;
+ *     b200ret_last_error() returns a thread-local message for the last failure.
+ *   - The library never allocates device memory: callers hand in a workspace whose size the matching
+ *     *_workspace_bytes() function reports (the Python host side uses torch's caching allocator).
+ *   - There is no CPU fallback anywhere: without a CUDA device every compute entry point fails.
+ */
+#ifndef B200RET_H
+#define B200RET_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200RET_VERSION 1
+
+#define B200RET_OK 0
+#define B200RET_EINVAL (-1)    /* bad argument (null pointer, size, alignment, k too large ...) */
+#define B200RET_ECUDA (-2)     /* a CUDA runtime call or kernel launch failed */
+#define B200RET_EWORKSPACE (-3)/* workspace too small */
+#define B200RET_EUNSORTED (-4) /* posting lists are not ascending in doc id (block table build) */
+#define B200RET_EOVERFLOW (-5) /* internal candidate buffer overflow that the safe schedule could not absorb */
+
+/* Largest top-k the select kernels support (shared-memory bound). */
+#define B200RET_MAX_K 4096
+
+int b200ret_version(void);
+const char* b200ret_last_error(void);
+
+/* Device facts the host side needs for grid sizing / sanity (cudaGetDeviceProperties). */
+int b200ret_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin_bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * (1) Sparse index build: COO -> CSR posting lists.
+ * Replaces IndexDictOfArray.add_batch_document (scaling_retriever/utils/inverted_index.py:67-76) and
+ * the array->numpy conversion of IndexDictOfArray.save (:84-88) / SparseIndexer.index
+ * (scaling_retriever/indexer.py:298-304).
+ *
+ * Input: `nnz` postings in FEED order (the order add_batch_document would have seen them):
+ *   rows[i] = document row id, cols[i] = term id in [0, n_terms), vals[i] = fp32 weight.
+ * Output (canonical CSR, bit-exact with the reference's per-term arrays):
+ *   term_offsets[n_terms + 1] (int64), doc_ids[nnz] (int32), weights[nnz] (fp32) with the postings of
+ *   term t at [term_offsets[t], term_offsets[t+1]) in FEED order (stable) when sort_docs == 0, or in
+ *   ascending doc-id order when sort_docs != 0 (what the search kernels need; identical to feed order
+ *   for the single-rank row-major feed of SparseIndexer.index).
+ * Implementation: hand-written stable LSD radix sort (match-any multisplit) + boundary scan.
+ * ---------------------------------------------------------------------------------------------- */
+size_t b200ret_csr_build_workspace_bytes(int64_t nnz, int32_t n_terms, int32_t n_docs, int sort_docs);
+
+int b200ret_csr_build(const int32_t* rows, const int32_t* cols, const float* vals, int64_t nnz,
+                      int32_t n_terms, int32_t n_docs, int sort_docs,
+                      int64_t* term_offsets, int32_t* doc_ids, float* weights,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Doc-block skip table over a doc-sorted CSR:  table[t * (n_blocks + 1) + b] = absolute position of
+ * the first posting of term t whose doc id is >= b * block_docs (b == n_blocks: term_offsets[t+1]).
+ * n_blocks = ceil(n_docs / block_docs).  No reference counterpart (the numba kernel walks whole
+ * lists, indexer.py:334-341); it lets one warp own a doc block and stream only its slice of a list.
+ * `status` is a device int32 the kernel sets to B200RET_EUNSORTED if a list is not ascending; the call
+ * synchronises the stream and returns that code.
+ * ---------------------------------------------------------------------------------------------- */
+int b200ret_block_table_build(const int64_t* term_offsets, const int32_t* doc_ids, int64_t nnz,
+                              int32_t n_terms, int32_t n_docs, int32_t block_docs,
+                              uint32_t* table, int32_t* status, void* stream);
+
+/* Doc-block size (documents per warp-private accumulator tile) compiled into the search kernel. */
+int32_t b200ret_sparse_block_docs(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2) Sparse query scoring + top-k for a batch of queries.
+ * Replaces SparseRetrieval.numba_score_float (scaling_retriever/indexer.py:324-344) followed by
+ * SparseRetrieval.select_topk (:315-322) for every query of _sparse_retrieve_multithreaded (:405-474).
+ *
+ * Queries are CSR-packed: query q owns q_terms/q_weights[q_offsets[q] .. q_offsets[q+1]) in the order
+ * the reference iterates them (ascending term id from torch.nonzero, indexer.py:396-401).
+ * Arithmetic is the reference's: per doc, fp32 `score += q_w * d_w` as a separate round-to-nearest
+ * multiply and add (no FMA) in query-term order -> scores are bit-identical to numba_score_float.
+ * Only docs with score > threshold are eligible (strict, indexer.py:342).
+ *
+ * Output per query q (row q of out_scores/out_ids, `k` columns): the out_counts[q] = min(k, #eligible)
+ * best docs sorted by (score descending, doc id ascending); unused tail slots hold (-inf, -1).
+ * Doc ids are LOCAL row ids + doc_id_base (shard offset for multi-GPU use).
+ * `n_docs` is the reference's size_collection.
+ * ---------------------------------------------------------------------------------------------- */
+size_t b200ret_sparse_search_workspace_bytes(int32_t n_queries, int32_t k);
+
+int b200ret_sparse_search(const uint32_t* table, const int32_t* doc_ids, const float* weights,
+                          int32_t n_terms, int32_t n_docs, int32_t block_docs,
+                          const int32_t* q_offsets, const int32_t* q_terms, const float* q_weights,
+                          int32_t n_queries, int32_t k, float threshold, int64_t doc_id_base,
+                          float* out_scores, int64_t* out_ids, int32_t* out_counts,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* Verification / API-parity entry point: the full fp32 score vector of every query, i.e. the `scores`
+ * array inside numba_score_float (indexer.py:332-341) before the threshold filter.
+ * out_scores: [n_queries][n_blocks * block_docs] (row stride padded to whole doc blocks; entries past
+ * n_docs are 0).  Same kernel, same arithmetic as b200ret_sparse_search.  workspace: >= 256 bytes. */
+int b200ret_sparse_scores(const uint32_t* table, const int32_t* doc_ids, const float* weights,
+                          int32_t n_terms, int32_t n_docs, int32_t block_docs,
+                          const int32_t* q_offsets, const int32_t* q_terms, const float* q_weights,
+                          int32_t n_queries, float* out_scores, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (3) Dense flat inner-product search.
+ * Replaces faiss.IndexFlatIP.search as called by DenseFlatIndexer.search_knn
+ * (scaling_retriever/indexer.py:210-214): exact top-k of Q . D^T, sorted descending.
+ * corpus: bf16 [n_docs, dim] row-major; queries: bf16 [n_queries, dim] row-major (bf16 storage,
+ * fp32 accumulation on tcgen05 tensor cores).  dim must be a multiple of 64.
+ * Output rows as in b200ret_sparse_search; unused tail slots hold (-inf, -1) (faiss pads with -1).
+ * ---------------------------------------------------------------------------------------------- */
+size_t b200ret_dense_search_workspace_bytes(int32_t n_queries, int32_t n_docs, int32_t dim, int32_t k);
+
+int b200ret_dense_search(const void* corpus_bf16, const void* queries_bf16,
+                         int32_t n_docs, int32_t n_queries, int32_t dim, int32_t k,
+                         int64_t doc_id_base,
+                         float* out_scores, int64_t* out_ids, int32_t* out_counts,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* fp32 -> bf16 (round-to-nearest-even) row conversion used when DenseFlatIndexer.index_data
+ * (indexer.py:198-208) ingests the fp32 .npy shards written by store_embs (:56-88). */
+int b200ret_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (4) Shard merge: G per-shard top-k lists (as produced above, gathered with an NCCL all-gather)
+ * -> one global top-k per query under the same total order (score desc, doc id asc).
+ * in_scores/in_ids: [G, n_queries, k] contiguous.  No reference counterpart: the reference asserts
+ * world_size == 1 for retrieval (eval_sparse.py:114, eval_dense.py:191).
+ * ---------------------------------------------------------------------------------------------- */
+int b200ret_merge_topk(const float* in_scores, const int64_t* in_ids, int32_t n_shards,
+                       int32_t n_queries, int32_t k,
+                       float* out_scores, int64_t* out_ids, int32_t* out_counts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RET_H */

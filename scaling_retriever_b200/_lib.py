@@ -1,0 +1,87 @@
+"""ctypes binding of libb200ret.so — the only way the Python host side reaches the CUDA kernels.
+
+Every prototype below mirrors include/b200ret.h.  Loading fails loudly (RuntimeError) when the library
+is absent and cannot be built: there is no CPU fallback and no alternative backend.
+"""
+import ctypes
+import os
+import threading
+
+from . import build as _build
+
+_c_i32 = ctypes.c_int32
+_c_i64 = ctypes.c_int64
+_c_f32 = ctypes.c_float
+_c_sz = ctypes.c_size_t
+_c_ptr = ctypes.c_void_p
+_c_int = ctypes.c_int
+
+# name -> (restype, argtypes); kept in one table so tests can check the exported symbol set.
+PROTOTYPES = {
+    "b200ret_version": (_c_int, []),
+    "b200ret_last_error": (ctypes.c_char_p, []),
+    "b200ret_device_info": (_c_int, [ctypes.POINTER(_c_int), ctypes.POINTER(_c_int), ctypes.POINTER(_c_int),
+                                     ctypes.POINTER(_c_sz)]),
+    "b200ret_csr_build_workspace_bytes": (_c_sz, [_c_i64, _c_i32, _c_i32, _c_int]),
+    "b200ret_csr_build": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i32, _c_i32, _c_int,
+                                   _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_sz, _c_ptr]),
+    "b200ret_block_table_build": (_c_int, [_c_ptr, _c_ptr, _c_i64, _c_i32, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_ptr]),
+    "b200ret_sparse_block_docs": (_c_i32, []),
+    "b200ret_sparse_search_workspace_bytes": (_c_sz, [_c_i32, _c_i32]),
+    "b200ret_sparse_search": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32,
+                                       _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_f32, _c_i64,
+                                       _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_sz, _c_ptr]),
+    "b200ret_sparse_scores": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32,
+                                       _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_ptr, _c_ptr, _c_sz, _c_ptr]),
+    "b200ret_dense_search_workspace_bytes": (_c_sz, [_c_i32, _c_i32, _c_i32, _c_i32]),
+    "b200ret_dense_search": (_c_int, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_i64,
+                                      _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_sz, _c_ptr]),
+    "b200ret_f32_to_bf16": (_c_int, [_c_ptr, _c_ptr, _c_i64, _c_ptr]),
+    "b200ret_merge_topk": (_c_int, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_ptr, _c_ptr]),
+}
+
+ERROR_NAMES = {-1: "EINVAL", -2: "ECUDA", -3: "EWORKSPACE", -4: "EUNSORTED", -5: "EOVERFLOW"}
+
+_lock = threading.Lock()
+_lib = None
+
+
+class B200RetError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"b200ret {ERROR_NAMES.get(code, code)}: {message}")
+        self.code = code
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Return the loaded CDLL (building it first if it is missing or stale and nvcc is available)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB_PATH
+        if not os.path.exists(path):
+            try:
+                _build.build()
+            except Exception as exc:  # no silent fallback: the CUDA library is the product
+                raise RuntimeError(
+                    f"libb200ret.so is missing at {path} and could not be built ({exc}). "
+                    "Run `python -m scaling_retriever_b200.build`; there is no CPU fallback.") from exc
+        lib = ctypes.CDLL(path)
+        for name, (restype, argtypes) in PROTOTYPES.items():
+            fn = getattr(lib, name)   # AttributeError if the .so does not export a declared symbol
+            fn.restype = restype
+            fn.argtypes = argtypes
+        if lib.b200ret_version() != 1:
+            raise RuntimeError(f"libb200ret.so version {lib.b200ret_version()} does not match the binding (1)")
+        _lib = lib
+        return _lib
+
+
+def check(code):
+    if code != 0:
+        msg = load().b200ret_last_error()
+        raise B200RetError(code, msg.decode() if msg else "")

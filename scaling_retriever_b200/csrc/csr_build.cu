@@ -1,0 +1,361 @@
+// Sparse index build on the GPU: COO postings -> CSR posting lists + doc-block skip table.
+//
+// Replaces the per-posting CPython loop of IndexDictOfArray.add_batch_document
+// (reference scaling_retriever/utils/inverted_index.py:67-76) and the list->ndarray conversion of
+// IndexDictOfArray.save (:84-88).  The reference appends (doc, value) to the list of term `col` in feed
+// order; that is exactly a STABLE sort of the posting stream by term id, so the build is a hand-written
+// stable LSD radix sort (<= 8 bits per pass, match-any warp multisplit, no atomics on the output order)
+// followed by a boundary scan that turns the sorted term column into term offsets.
+//
+// HBM-bound integer/byte work: every pass streams 12 B/posting in (coalesced, one posting per lane)
+// and 12 B/posting out; the grid is persistent (a multiple of the SM count) so the per-pass digit
+// table is tiny (buckets x blocks) and one CTA scans it.
+#include "common.cuh"
+
+namespace b200ret {
+
+constexpr int SORT_THREADS = 512;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_ROUNDS = 8;                                  // postings per lane per tile
+constexpr int SORT_TILE = SORT_THREADS * SORT_ROUNDS;           // 4096 postings per tile
+constexpr int SORT_MAX_BUCKETS = 256;
+
+struct SortPass {
+    const int32_t* src_row;
+    const int32_t* src_col;
+    const float* src_val;
+    int32_t* dst_row;
+    int32_t* dst_col;
+    float* dst_val;
+    int key_is_row;   // digit taken from the row (doc) column instead of the term column
+    int shift;
+    int bits;
+};
+
+__device__ __forceinline__ uint32_t pass_digit(const SortPass& p, int32_t row, int32_t col) {
+    uint32_t key = static_cast<uint32_t>(p.key_is_row ? row : col);
+    return (key >> p.shift) & ((1u << p.bits) - 1u);
+}
+
+// Block b owns postings [b * per_block, min(nnz, (b + 1) * per_block)); per_block is a multiple of SORT_TILE.
+__global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(SortPass p, int64_t nnz, int64_t per_block,
+                                                                 uint32_t* __restrict__ counts) {
+    __shared__ uint32_t hist[SORT_MAX_BUCKETS];
+    const int buckets = 1 << p.bits;
+    for (int i = threadIdx.x; i < buckets; i += SORT_THREADS) hist[i] = 0;
+    __syncthreads();
+    const int64_t lo = static_cast<int64_t>(blockIdx.x) * per_block;
+    const int64_t hi = min(nnz, lo + per_block);
+    const int32_t* keys = p.key_is_row ? p.src_row : p.src_col;
+    const uint32_t mask = (1u << p.bits) - 1u;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += SORT_THREADS) {
+        uint32_t d = (static_cast<uint32_t>(__ldg(keys + i)) >> p.shift) & mask;
+        // Warp-aggregate equal digits before touching shared memory (Zipfian term ids collide a lot).
+        unsigned peers = __match_any_sync(__activemask(), d);
+        if ((peers & lanemask_lt()) == 0) atomicAdd(&hist[d], __popc(peers));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < buckets; i += SORT_THREADS) counts[static_cast<size_t>(i) * gridDim.x + blockIdx.x] = hist[i];
+}
+
+// Exclusive scan of counts[bucket][block] (bucket-major) in place; one CTA, sequential chunks per thread.
+__global__ void __launch_bounds__(1024) sort_scan_kernel(uint32_t* __restrict__ counts, int n) {
+    __shared__ uint32_t partial[1024];
+    const int per = (n + 1023) / 1024;
+    const int lo = min(n, static_cast<int>(threadIdx.x) * per);
+    const int hi = min(n, lo + per);
+    uint32_t sum = 0;
+    for (int i = lo; i < hi; ++i) sum += counts[i];
+    partial[threadIdx.x] = sum;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over the 1024 partials.
+    for (int off = 1; off < 1024; off <<= 1) {
+        uint32_t v = (threadIdx.x >= off) ? partial[threadIdx.x - off] : 0;
+        __syncthreads();
+        partial[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = partial[threadIdx.x] - sum;
+    for (int i = lo; i < hi; ++i) {
+        uint32_t c = counts[i];
+        counts[i] = run;
+        run += c;
+    }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(SortPass p, int64_t nnz, int64_t per_block,
+                                                                    const uint32_t* __restrict__ bases) {
+    __shared__ uint32_t wcnt[SORT_WARPS][SORT_MAX_BUCKETS];
+    __shared__ uint32_t gbase[SORT_MAX_BUCKETS];
+    const int buckets = 1 << p.bits;
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < buckets; i += SORT_THREADS) gbase[i] = bases[static_cast<size_t>(i) * gridDim.x + blockIdx.x];
+
+    const int64_t lo = static_cast<int64_t>(blockIdx.x) * per_block;
+    const int64_t hi = min(nnz, lo + per_block);
+    for (int64_t tile = lo; tile < hi; tile += SORT_TILE) {
+        for (int i = threadIdx.x; i < SORT_WARPS * buckets; i += SORT_THREADS) wcnt[i / buckets][i % buckets] = 0;
+        __syncthreads();
+
+        int32_t row[SORT_ROUNDS], col[SORT_ROUNDS];
+        float val[SORT_ROUNDS];
+        uint32_t rank[SORT_ROUNDS], dig[SORT_ROUNDS];
+        // Warp w owns the contiguous slice [tile + w*256, +256): round-major, lane-minor == feed order.
+        const int64_t wbase = tile + static_cast<int64_t>(warp) * (32 * SORT_ROUNDS);
+#pragma unroll
+        for (int r = 0; r < SORT_ROUNDS; ++r) {
+            const int64_t i = wbase + r * 32 + lane;
+            const bool valid = i < hi;
+            row[r] = valid ? __ldg(p.src_row + i) : 0;
+            col[r] = valid ? __ldg(p.src_col + i) : 0;
+            val[r] = valid ? __ldg(p.src_val + i) : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < SORT_ROUNDS; ++r) {
+            const bool valid = (wbase + r * 32 + lane) < hi;
+            const uint32_t d = valid ? pass_digit(p, row[r], col[r]) : 0xffffffffu;
+            dig[r] = d;
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            const unsigned before = __popc(peers & lanemask_lt());
+            uint32_t old = 0;
+            if (valid && before == 0) {   // lowest lane of each digit group bumps the warp-private counter
+                old = wcnt[warp][d];
+                wcnt[warp][d] = old + __popc(peers);
+            }
+            old = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1);
+            rank[r] = old + before;
+            __syncwarp();
+        }
+        __syncthreads();
+        // Per digit: exclusive scan over warps, rebased on the block's running global offset.
+        for (int d = threadIdx.x; d < buckets; d += SORT_THREADS) {
+            uint32_t run = gbase[d];
+#pragma unroll
+            for (int w = 0; w < SORT_WARPS; ++w) {
+                uint32_t c = wcnt[w][d];
+                wcnt[w][d] = run;
+                run += c;
+            }
+            gbase[d] = run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < SORT_ROUNDS; ++r) {
+            if (dig[r] != 0xffffffffu) {
+                const uint32_t pos = wcnt[warp][dig[r]] + rank[r];
+                p.dst_row[pos] = row[r];
+                p.dst_col[pos] = col[r];
+                p.dst_val[pos] = val[r];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// term_offsets from the sorted term column: thread i fills offsets (prev_term, cur_term] = i.
+__global__ void term_offsets_kernel(const int32_t* __restrict__ sorted_col, int64_t nnz, int32_t n_terms,
+                                    int64_t* __restrict__ term_offsets) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nnz; i += stride) {
+        const int32_t cur = sorted_col[i];
+        const int32_t prev = (i > 0) ? sorted_col[i - 1] : -1;
+        for (int32_t t = prev + 1; t <= cur; ++t) term_offsets[t] = i;
+        if (i == nnz - 1)
+            for (int32_t t = cur + 1; t <= n_terms; ++t) term_offsets[t] = nnz;
+    }
+}
+
+__global__ void fill_i64_kernel(int64_t* p, int64_t n, int64_t v) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// ---- doc-block skip table ------------------------------------------------------------------------
+
+__device__ __forceinline__ int32_t term_of_posting(const int64_t* __restrict__ term_offsets, int32_t n_terms, int64_t i) {
+    // largest t with term_offsets[t] <= i  (upper_bound - 1); empty terms are skipped automatically.
+    int32_t lo = 0, hi = n_terms;   // answer in [lo, hi)
+    while (hi - lo > 1) {
+        int32_t mid = (lo + hi) >> 1;
+        if (__ldg(term_offsets + mid) <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void block_table_kernel(const int64_t* __restrict__ term_offsets, const int32_t* __restrict__ doc_ids,
+                                   int64_t nnz, int32_t n_terms, int32_t block_docs, int32_t n_blocks,
+                                   uint32_t* __restrict__ table, int32_t* __restrict__ status) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    const size_t row_len = static_cast<size_t>(n_blocks) + 1;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nnz; i += stride) {
+        const int32_t t = term_of_posting(term_offsets, n_terms, i);
+        const int64_t beg = __ldg(term_offsets + t), end = __ldg(term_offsets + t + 1);
+        const int32_t d = __ldg(doc_ids + i);
+        const int32_t b = d / block_docs;
+        int32_t b_prev = -1;
+        if (i > beg) {
+            const int32_t dp = __ldg(doc_ids + i - 1);
+            b_prev = dp / block_docs;
+            if (dp > d) *status = B200RET_EUNSORTED;
+        }
+        if (b >= n_blocks || d < 0) { *status = B200RET_EINVAL; continue; }
+        uint32_t* row = table + static_cast<size_t>(t) * row_len;
+        for (int32_t bb = b_prev + 1; bb <= b; ++bb) row[bb] = static_cast<uint32_t>(i);
+        if (i + 1 == end)
+            for (int32_t bb = b + 1; bb <= n_blocks; ++bb) row[bb] = static_cast<uint32_t>(i + 1);
+    }
+}
+
+// Rows of empty terms: every entry is the (shared) list position.  One warp per term.
+__global__ void block_table_empty_kernel(const int64_t* __restrict__ term_offsets, int32_t n_terms, int32_t n_blocks,
+                                         uint32_t* __restrict__ table) {
+    const int warps_per_block = blockDim.x >> 5;
+    const int lane = lane_id();
+    for (int32_t t = blockIdx.x * warps_per_block + (threadIdx.x >> 5); t < n_terms; t += gridDim.x * warps_per_block) {
+        const int64_t beg = term_offsets[t];
+        if (term_offsets[t + 1] != beg) continue;
+        uint32_t* row = table + static_cast<size_t>(t) * (static_cast<size_t>(n_blocks) + 1);
+        for (int32_t bb = lane; bb <= n_blocks; bb += 32) row[bb] = static_cast<uint32_t>(beg);
+    }
+}
+
+static int bits_for(int64_t n_values) {   // bits needed to represent values in [0, n_values)
+    int b = 0;
+    while ((int64_t{1} << b) < n_values) ++b;
+    return b < 1 ? 1 : b;
+}
+
+struct PassPlan {
+    int n;
+    int key_is_row[16];
+    int shift[16];
+    int bits[16];
+};
+
+static void plan_bits(PassPlan& plan, int total_bits, int key_is_row) {
+    const int passes = (total_bits + 7) / 8;
+    int done = 0;
+    for (int i = 0; i < passes; ++i) {
+        int b = (total_bits - done + (passes - i) - 1) / (passes - i);   // spread evenly, <= 8
+        plan.key_is_row[plan.n] = key_is_row;
+        plan.shift[plan.n] = done;
+        plan.bits[plan.n] = b;
+        ++plan.n;
+        done += b;
+    }
+}
+
+static PassPlan make_plan(int32_t n_terms, int32_t n_docs, int sort_docs) {
+    PassPlan plan{};
+    if (sort_docs) plan_bits(plan, bits_for(n_docs), 1);   // least significant key first (LSD)
+    plan_bits(plan, bits_for(n_terms), 0);
+    return plan;
+}
+
+static int sort_grid() { return sm_count() * 2; }
+
+}  // namespace b200ret
+
+using namespace b200ret;
+
+extern "C" size_t b200ret_csr_build_workspace_bytes(int64_t nnz, int32_t n_terms, int32_t n_docs, int sort_docs) {
+    (void)n_terms; (void)n_docs; (void)sort_docs;
+    const size_t n = static_cast<size_t>(nnz > 0 ? nnz : 1);
+    // two ping-pong (row, col, val) triples + the bucket x block digit table
+    size_t bytes = 0;
+    for (int i = 0; i < 6; ++i) bytes += align_up(n * 4, 256);
+    bytes += align_up(static_cast<size_t>(SORT_MAX_BUCKETS) * sort_grid() * sizeof(uint32_t), 256);
+    return bytes + 256;
+}
+
+extern "C" int b200ret_csr_build(const int32_t* rows, const int32_t* cols, const float* vals, int64_t nnz,
+                                 int32_t n_terms, int32_t n_docs, int sort_docs,
+                                 int64_t* term_offsets, int32_t* doc_ids, float* weights,
+                                 void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    B200RET_REQUIRE(nnz >= 0 && n_terms > 0 && n_docs >= 0, "csr_build: bad sizes nnz=%lld n_terms=%d n_docs=%d",
+                    (long long)nnz, n_terms, n_docs);
+    B200RET_REQUIRE(nnz < (int64_t{1} << 32) - SORT_TILE, "csr_build: nnz=%lld exceeds the 32-bit position range",
+                    (long long)nnz);
+    B200RET_REQUIRE(term_offsets != nullptr, "csr_build: term_offsets is null");
+    if (nnz == 0) {
+        const int64_t n = static_cast<int64_t>(n_terms) + 1;
+        fill_i64_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(term_offsets, n, 0);
+        B200RET_CUDA_CHECK(cudaGetLastError());
+        return B200RET_OK;
+    }
+    B200RET_REQUIRE(rows && cols && vals && doc_ids && weights && workspace, "csr_build: null pointer");
+    if (workspace_bytes < b200ret_csr_build_workspace_bytes(nnz, n_terms, n_docs, sort_docs)) {
+        set_err("csr_build: workspace too small (%zu bytes)", workspace_bytes);
+        return B200RET_EWORKSPACE;
+    }
+    Workspace ws(workspace, workspace_bytes);
+    int32_t* a_row = ws.take<int32_t>(nnz);
+    int32_t* a_col = ws.take<int32_t>(nnz);
+    float* a_val = ws.take<float>(nnz);
+    int32_t* b_row = ws.take<int32_t>(nnz);
+    int32_t* b_col = ws.take<int32_t>(nnz);
+    float* b_val = ws.take<float>(nnz);
+    const int grid = sort_grid();
+    uint32_t* counts = ws.take<uint32_t>(static_cast<size_t>(SORT_MAX_BUCKETS) * grid);
+
+    int64_t per_block = (nnz + grid - 1) / grid;
+    per_block = (per_block + SORT_TILE - 1) / SORT_TILE * SORT_TILE;
+
+    const PassPlan plan = make_plan(n_terms, n_docs, sort_docs);
+    const int32_t* src_row = rows;
+    const int32_t* src_col = cols;
+    const float* src_val = vals;
+    const int32_t* sorted_col = nullptr;
+    for (int i = 0; i < plan.n; ++i) {
+        const bool last = (i == plan.n - 1);
+        const bool to_a = (i % 2 == 0);
+        SortPass p;
+        p.src_row = src_row; p.src_col = src_col; p.src_val = src_val;
+        p.dst_row = last ? doc_ids : (to_a ? a_row : b_row);
+        p.dst_col = to_a ? a_col : b_col;
+        p.dst_val = last ? weights : (to_a ? a_val : b_val);
+        p.key_is_row = plan.key_is_row[i]; p.shift = plan.shift[i]; p.bits = plan.bits[i];
+        const int buckets = 1 << p.bits;
+        sort_hist_kernel<<<grid, SORT_THREADS, 0, stream>>>(p, nnz, per_block, counts);
+        sort_scan_kernel<<<1, 1024, 0, stream>>>(counts, buckets * grid);
+        sort_scatter_kernel<<<grid, SORT_THREADS, 0, stream>>>(p, nnz, per_block, counts);
+        B200RET_CUDA_CHECK(cudaGetLastError());
+        src_row = p.dst_row; src_col = p.dst_col; src_val = p.dst_val;
+        sorted_col = p.dst_col;
+    }
+    term_offsets_kernel<<<sm_count() * 8, 256, 0, stream>>>(sorted_col, nnz, n_terms, term_offsets);
+    B200RET_CUDA_CHECK(cudaGetLastError());
+    return B200RET_OK;
+}
+
+extern "C" int b200ret_block_table_build(const int64_t* term_offsets, const int32_t* doc_ids, int64_t nnz,
+                                         int32_t n_terms, int32_t n_docs, int32_t block_docs,
+                                         uint32_t* table, int32_t* status, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    B200RET_REQUIRE(term_offsets && table && status, "block_table_build: null pointer");
+    B200RET_REQUIRE(n_terms > 0 && n_docs >= 0 && block_docs > 0 && nnz >= 0, "block_table_build: bad sizes");
+    B200RET_REQUIRE(nnz < (int64_t{1} << 32), "block_table_build: nnz exceeds 32-bit positions");
+    const int32_t n_blocks = (n_docs + block_docs - 1) / block_docs;
+    B200RET_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int32_t), stream));
+    block_table_empty_kernel<<<sm_count() * 4, 256, 0, stream>>>(term_offsets, n_terms, n_blocks, table);
+    if (nnz > 0) {
+        B200RET_REQUIRE(doc_ids != nullptr, "block_table_build: doc_ids is null");
+        block_table_kernel<<<sm_count() * 8, 256, 0, stream>>>(term_offsets, doc_ids, nnz, n_terms, block_docs, n_blocks,
+                                                               table, status);
+    }
+    B200RET_CUDA_CHECK(cudaGetLastError());
+    int32_t host_status = 0;
+    B200RET_CUDA_CHECK(cudaMemcpyAsync(&host_status, status, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    B200RET_CUDA_CHECK(cudaStreamSynchronize(stream));
+    if (host_status == B200RET_EUNSORTED) {
+        set_err("block_table_build: a posting list is not ascending in doc id (build the CSR with sort_docs=1)");
+        return B200RET_EUNSORTED;
+    }
+    if (host_status != 0) {
+        set_err("block_table_build: doc id out of range [0, n_docs)");
+        return B200RET_EINVAL;
+    }
+    return B200RET_OK;
+}

@@ -1,0 +1,109 @@
+// Shard merge: G per-shard top-k rows -> one global top-k row per query, plus the fp32->bf16 ingest cast.
+//
+// The reference never searches shards in parallel (retrieval asserts world_size == 1,
+// eval_sparse.py:114 / eval_dense.py:191); this is the reduce step of the doc-range sharded search:
+// every rank all-gathers [Q, k] (score, id) rows over NCCL and runs this kernel locally.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "topk_select.cuh"
+
+namespace b200ret {
+
+constexpr int MERGE_THREADS = 512;
+constexpr int MERGE_MAX_CANDIDATES = 16384;   // 128 KB of keys in shared memory
+
+__global__ void __launch_bounds__(MERGE_THREADS) merge_topk_kernel(const float* __restrict__ in_scores,
+                                                                   const int64_t* __restrict__ in_ids, int32_t n_shards,
+                                                                   int32_t n_queries, int32_t k, float* out_scores,
+                                                                   int64_t* out_ids, int32_t* out_counts) {
+    extern __shared__ __align__(16) uint64_t skeys[];
+    __shared__ uint32_t hist[256];
+    __shared__ uint64_t bcast[2];
+    __shared__ int n_live;
+    const int q = blockIdx.x;
+    if (threadIdx.x == 0) n_live = 0;
+    __syncthreads();
+    // Gather the live (id >= 0) candidates of all shards.  Global ids fit 31 bits (checked on the host).
+    const int total = n_shards * k;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int g = i / k, j = i % k;
+        const size_t src = (static_cast<size_t>(g) * n_queries + q) * k + j;
+        const int64_t id = in_ids[src];
+        if (id >= 0) skeys[atomicAdd(&n_live, 1)] = cand_key(in_scores[src], static_cast<int32_t>(id));
+    }
+    __syncthreads();
+    const int c = n_live;
+    int kept = c;
+    uint64_t kth = 0;
+    if (c > k) {
+        kth = block_radix_select_kth(skeys, c, k, hist, bcast);
+        kept = k;
+    }
+    // Keys below the cut become 0 (sorts last); then one descending sort of the padded array.
+    const int n_sort = next_pow2(max(c, 1));
+    for (int i = threadIdx.x; i < n_sort; i += blockDim.x)
+        if (i >= c || skeys[i] < kth) skeys[i] = 0;
+    block_bitonic_sort_desc(skeys, n_sort);
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const bool live = i < kept;
+        const uint64_t key = live ? skeys[i] : 0;
+        out_scores[static_cast<size_t>(q) * k + i] = live ? cand_score(key) : -INFINITY;
+        out_ids[static_cast<size_t>(q) * k + i] = live ? static_cast<int64_t>(cand_id(key)) : -1;
+    }
+    if (threadIdx.x == 0) out_counts[q] = kept;
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 4;
+    for (int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        if (i + 4 <= n) {
+            const float4 v = *reinterpret_cast<const float4*>(src + i);
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
+            __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+            uint2 packed;
+            packed.x = *reinterpret_cast<uint32_t*>(&lo);
+            packed.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(dst + i) = packed;
+        } else {
+            for (int64_t j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+        }
+    }
+}
+
+}  // namespace b200ret
+
+using namespace b200ret;
+
+extern "C" int b200ret_merge_topk(const float* in_scores, const int64_t* in_ids, int32_t n_shards, int32_t n_queries,
+                                  int32_t k, float* out_scores, int64_t* out_ids, int32_t* out_counts, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    B200RET_REQUIRE(n_shards >= 1 && n_queries >= 0 && k >= 1, "merge_topk: bad sizes");
+    B200RET_REQUIRE(static_cast<int64_t>(n_shards) * k <= MERGE_MAX_CANDIDATES,
+                    "merge_topk: n_shards*k=%lld exceeds %d candidates per query", (long long)n_shards * k, MERGE_MAX_CANDIDATES);
+    if (n_queries == 0) return B200RET_OK;
+    B200RET_REQUIRE(in_scores && in_ids && out_scores && out_ids && out_counts, "merge_topk: null pointer");
+    const size_t smem = static_cast<size_t>(next_pow2(n_shards * k)) * sizeof(uint64_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        B200RET_CUDA_CHECK(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                MERGE_MAX_CANDIDATES * (int)sizeof(uint64_t)));
+        attr_set = true;
+    }
+    merge_topk_kernel<<<n_queries, MERGE_THREADS, smem, stream>>>(in_scores, in_ids, n_shards, n_queries, k, out_scores,
+                                                                  out_ids, out_counts);
+    B200RET_CUDA_CHECK(cudaGetLastError());
+    return B200RET_OK;
+}
+
+extern "C" int b200ret_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    B200RET_REQUIRE(n >= 0, "f32_to_bf16: negative size");
+    if (n == 0) return B200RET_OK;
+    B200RET_REQUIRE(src && dst_bf16, "f32_to_bf16: null pointer");
+    B200RET_REQUIRE((reinterpret_cast<uintptr_t>(src) % 16 == 0) && (reinterpret_cast<uintptr_t>(dst_bf16) % 8 == 0),
+                    "f32_to_bf16: pointers must be 16/8-byte aligned");
+    f32_to_bf16_kernel<<<sm_count() * 8, 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst_bf16), n);
+    B200RET_CUDA_CHECK(cudaGetLastError());
+    return B200RET_OK;
+}

@@ -1,0 +1,93 @@
+// Block-level exact top-k over 64-bit candidate keys held in shared memory.
+//
+// A candidate is (fp32 score, int32 doc id) packed by cand_key() so that key order == (score desc,
+// doc id asc).  Keys are unique (doc ids are), which makes the k-th largest key a total cut: the
+// result set is deterministic whatever order the candidates were appended in.  This is the GPU
+// replacement for np.argpartition in SparseRetrieval.select_topk (reference
+// scaling_retriever/indexer.py:315-322) and for faiss's reservoir collector behind
+// IndexFlatIP.search (:211); unlike argpartition it resolves boundary ties deterministically
+// (lowest doc id wins).
+#pragma once
+#include "common.cuh"
+
+namespace b200ret {
+
+// MSB-first 8-bit radix select: returns the k-th largest key (1 <= k <= n) of keys[0..n).
+// `hist` is 256 shared counters, `bcast` two shared u64 slots.  All threads of the block call it.
+__device__ inline uint64_t block_radix_select_kth(const uint64_t* keys, int n, int k, uint32_t* hist,
+                                                  uint64_t* bcast) {
+    uint64_t prefix = 0, mask = 0;
+    int remaining = k;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint64_t key = keys[i];
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xff], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            // Warp 0 walks the 256 buckets from the top, 8 buckets per lane (lane 0 = highest digits).
+            uint32_t c[8];
+            uint32_t local = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                c[j] = hist[255 - (threadIdx.x * 8 + j)];
+                local += c[j];
+            }
+            uint32_t incl = local;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+                if (static_cast<int>(threadIdx.x) >= off) incl += v;
+            }
+            uint32_t above = incl - local;   // candidates in strictly higher buckets than this lane's
+            if (above < static_cast<uint32_t>(remaining) && incl >= static_cast<uint32_t>(remaining)) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (above + c[j] >= static_cast<uint32_t>(remaining)) {
+                        bcast[0] = static_cast<uint64_t>(255 - (threadIdx.x * 8 + j));
+                        bcast[1] = static_cast<uint64_t>(remaining - above);
+                        break;
+                    }
+                    above += c[j];
+                }
+            }
+        }
+        __syncthreads();
+        const uint64_t digit = bcast[0];
+        remaining = static_cast<int>(bcast[1]);
+        prefix |= digit << shift;
+        mask |= 0xffull << shift;
+        __syncthreads();
+    }
+    return prefix;
+}
+
+// In-place bitonic sort, DESCENDING, of keys[0..n_pow2) (n_pow2 a power of two; pad with 0).
+__device__ inline void block_bitonic_sort_desc(uint64_t* keys, int n_pow2) {
+    for (int size = 2; size <= n_pow2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < (n_pow2 >> 1); i += blockDim.x) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = ((lo & size) == 0);
+                const uint64_t a = keys[lo], b = keys[hi];
+                if ((a < b) == desc) {
+                    keys[lo] = b;
+                    keys[hi] = a;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__host__ __device__ inline int next_pow2(int n) {
+    int p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+}  // namespace b200ret

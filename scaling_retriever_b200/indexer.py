@@ -1,0 +1,457 @@
+"""B200-native drop-in for the retrieval engine of scaling_retriever/indexer.py (reference).
+
+Same public names, constructor arguments, return values and side-effect files as the reference module, so
+eval_sparse.py (:104-106, :149-151) and eval_dense.py (:188, :193-199, :223-227) drive it unchanged:
+
+    store_embs · DenseIndexer · DenseFlatIndexer · SparseIndexer · SparseRetrieval
+
+What moved to the GPU (hand-written sm_100a kernels behind include/b200ret.h, bound in ops.py):
+  * SparseIndexer.index / IndexDictOfArray.add_batch_document: COO batches stay on the device, one radix-sort CSR build;
+  * SparseRetrieval._sparse_retrieve_multithreaded: the numba scorer + argpartition become one batched search call;
+  * DenseFlatIndexer.index_data / search_knn: faiss.IndexFlatIP becomes a bf16 corpus in HBM + a fused GEMM/top-k kernel.
+There is no CPU fallback: constructing a retriever or indexer without a CUDA device raises.
+"""
+import json
+import logging
+import os
+import pickle
+from collections import defaultdict
+from typing import List, Tuple
+
+import numpy as np
+import torch
+from tqdm import tqdm
+
+from . import ops, shard
+from .inverted_index import IndexDictOfArray
+from .utils import is_first_worker, obtain_doc_vec_dir_files, rank as _rank, supports_bfloat16, to_list, world_size as _world_size
+
+logger = logging.getLogger()
+
+
+def _unwrap_model(model):
+    # transformers.modeling_utils.unwrap_model (used by the reference, indexer.py:10,52) without the import cost
+    while hasattr(model, "module"):
+        model = model.module
+    return model
+
+
+class L0:
+    """non-differentiable (reference modeling/losses/regulariaztion.py:9-14)"""
+
+    def __call__(self, batch_rep):
+        return torch.count_nonzero(batch_rep, dim=-1).float().mean()
+
+
+def _cuda_device(device):
+    if not torch.cuda.is_available():
+        raise RuntimeError("the B200 retrieval engine needs a CUDA device; there is no CPU fallback")
+    if isinstance(device, torch.device):
+        return device if device.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
+    if isinstance(device, int):
+        return torch.device("cuda", device)
+    if isinstance(device, str) and device.startswith("cuda"):
+        return torch.device(device)
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# dense: embeddings dump (unchanged format) + flat inner-product index
+# ------------------------------------------------------------------------------------------------------------------
+
+def store_embs(model, collection_loader, local_rank, index_dir, device,
+               chunk_size=2_000_000, use_fp16=False, is_query=False, idx_to_id=None):
+    """Encode the corpus and write embs_{rank}_{chunk}.npy / ids_{rank}_{chunk}.npy / plan.json (reference
+    indexer.py:26-97).  The on-disk format is the dense index INPUT and is kept byte-compatible."""
+    write_freq = chunk_size // collection_loader.batch_size
+    if is_first_worker():
+        print("write_freq: {}, batch_size: {}, chunk_size: {}".format(write_freq, collection_loader.batch_size, chunk_size))
+    dtype = torch.bfloat16 if supports_bfloat16() else torch.float32
+    print("Using bfloat16" if dtype == torch.bfloat16 else "Using float32")
+
+    def flush(embeddings, embeddings_ids, chunk_idx):
+        embeddings = np.concatenate(embeddings)
+        if isinstance(embeddings_ids[0], int):
+            embeddings_ids = np.array(embeddings_ids, dtype=np.int64)
+        assert len(embeddings) == len(embeddings_ids), (len(embeddings), len(embeddings_ids))
+        np.save(os.path.join(index_dir, "embs_{}_{}.npy".format(local_rank, chunk_idx)), embeddings)
+        np.save(os.path.join(index_dir, "ids_{}_{}.npy".format(local_rank, chunk_idx)), embeddings_ids)
+
+    embeddings, embeddings_ids, chunk_idx = [], [], 0
+    for idx, batch in tqdm(enumerate(collection_loader), disable=not is_first_worker(),
+                           desc=f"encode # {len(collection_loader)} seqs", total=len(collection_loader)):
+        with torch.inference_mode():
+            with torch.amp.autocast("cuda", dtype=dtype):
+                inputs = {k: v.to(device) for k, v in batch.items() if k != "ids"}
+                if is_query:
+                    raise NotImplementedError
+                reps = _unwrap_model(model).doc_encode(**inputs)
+                text_ids = batch["ids"]
+        embeddings.append(reps.float().cpu().numpy())
+        assert isinstance(text_ids, list)
+        embeddings_ids.extend(text_ids)
+        if (idx + 1) % write_freq == 0:
+            flush(embeddings, embeddings_ids, chunk_idx)
+            embeddings, embeddings_ids = [], []
+            chunk_idx += 1
+    if len(embeddings) != 0:
+        print("last embedddings shape = {}".format(np.concatenate(embeddings).shape))
+        flush(embeddings, embeddings_ids, chunk_idx)
+        chunk_idx += 1
+
+    plan = {"nranks": _world_size(), "num_chunks": chunk_idx, "index_path": os.path.join(index_dir, "model.index")}
+    print("plan: ", plan)
+    if is_first_worker():
+        with open(os.path.join(index_dir, "plan.json"), "w") as fout:
+            json.dump(plan, fout)
+
+
+class DenseIndexer(object):
+    """Base class with the reference's (de)serialisation surface (indexer.py:127-188).  `self.index` is a bf16 CUDA
+    tensor [N, d] instead of a faiss object; index.dpr is a .npy of its raw uint16 words, index_meta.dpr the pickled
+    id list exactly as in the reference."""
+
+    def __init__(self, buffer_size: int = 50000):
+        self.buffer_size = buffer_size
+        self.index_id_to_db_id = []
+        self.index = None
+
+    def init_index(self, vector_sz: int):
+        raise NotImplementedError
+
+    def index_data(self, data: List[Tuple[object, np.array]]):
+        raise NotImplementedError
+
+    def get_index_name(self):
+        raise NotImplementedError
+
+    def search_knn(self, query_vectors: np.array, top_docs: int):
+        raise NotImplementedError
+
+    def serialize(self, file: str):
+        logger.info("Serializing index to %s", file)
+        if os.path.isdir(file):
+            index_file = os.path.join(file, "index.dpr")
+            meta_file = os.path.join(file, "index_meta.dpr")
+        else:
+            index_file = file + ".index.dpr"
+            meta_file = file + ".index_meta.dpr"
+        with open(index_file, "wb") as f:
+            np.save(f, self.index.view(torch.int16).cpu().numpy())
+        with open(meta_file, mode="wb") as f:
+            pickle.dump(self.index_id_to_db_id, f)
+
+    def get_files(self, path: str):
+        if os.path.isdir(path):
+            index_file = os.path.join(path, "index.dpr")
+            meta_file = os.path.join(path, "index_meta.dpr")
+        else:
+            index_file = path + ".{}.dpr".format(self.get_index_name())
+            meta_file = path + ".{}_meta.dpr".format(self.get_index_name())
+        return index_file, meta_file
+
+    def index_exists(self, path: str):
+        index_file, meta_file = self.get_files(path)
+        return os.path.isfile(index_file) and os.path.isfile(meta_file)
+
+    def deserialize(self, path: str):
+        logger.info("Loading index from %s", path)
+        index_file, meta_file = self.get_files(path)
+        with open(index_file, "rb") as f:
+            words = np.load(f)
+        self.index = torch.from_numpy(words).to(_cuda_device(None)).view(torch.bfloat16)
+        logger.info("Loaded index of type %s and size %d", type(self.index), self.index.shape[0])
+        with open(meta_file, "rb") as reader:
+            self.index_id_to_db_id = pickle.load(reader)
+        assert len(self.index_id_to_db_id) == self.index.shape[0], "Deserialized index_id_to_db_id should match index size"
+
+    def _update_id_mapping(self, db_ids: List):
+        self.index_id_to_db_id.extend(db_ids)
+        return len(self.index_id_to_db_id)
+
+
+class DenseFlatIndexer(DenseIndexer):
+    """Exact inner-product index (reference indexer.py:191-217, faiss.IndexFlatIP): the corpus lives in HBM as bf16
+    [N, d]; search is the fused tcgen05 GEMM + top-k kernel (ops.dense_search).  Under torch.distributed with
+    world_size > 1 each rank keeps the doc-row range shard.ShardPlan assigns it and results are merged after an
+    all-gather."""
+
+    def __init__(self, buffer_size: int = 50000, device=None):
+        super().__init__(buffer_size)
+        self.device = device
+        self.hidden_dim = None
+        self._row_lo = 0
+
+    def init_index(self, hidden_dim):
+        self.device = _cuda_device(self.device)
+        self.hidden_dim = int(hidden_dim)
+        self.index = torch.empty((0, self.hidden_dim), dtype=torch.bfloat16, device=self.device)
+
+    def index_data(self, doc_reps, doc_ids):
+        assert len(doc_reps) == len(doc_ids)
+        n = len(doc_reps)
+        plan = shard.ShardPlan(n, _world_size())
+        lo, hi = plan.bounds(_rank())
+        self._row_lo = lo
+        corpus = torch.empty((hi - lo, self.hidden_dim), dtype=torch.bfloat16, device=self.device)
+        n_total = 0
+        for i in tqdm(range(0, n, self.buffer_size), total=n // self.buffer_size, desc="indexing", disable=not is_first_worker()):
+            a, b = max(i, lo), min(i + self.buffer_size, hi)
+            if a < b:   # this slice (partly) belongs to our shard: host fp32 -> device -> bf16 cast kernel
+                chunk = torch.from_numpy(np.ascontiguousarray(doc_reps[a:b], dtype=np.float32)).to(self.device)
+                corpus[a - lo:b - lo] = ops.f32_to_bf16(chunk)
+            n_total = self._update_id_mapping(doc_ids[i:i + self.buffer_size])
+            logger.info("data indexed %d", n_total)
+        assert n_total == n, (n_total, n)
+        self.index = corpus
+        logger.info("total data indexed %d", n_total)
+
+    def search_arrays(self, query_reps, top_docs):
+        """(scores fp32 [Q, k] descending, row labels int64 [Q, k], -1 padded) as host numpy arrays."""
+        q = torch.from_numpy(np.ascontiguousarray(query_reps, dtype=np.float32)).to(self.device)
+        q16 = ops.f32_to_bf16(q)
+        scores, ids, _ = ops.dense_search(self.index, q16, int(top_docs), doc_id_base=self._row_lo)
+        if _world_size() > 1:
+            scores, ids, _ = shard.merge_shards(scores, ids, int(top_docs))
+        return scores.cpu().numpy(), ids.cpu().numpy()
+
+    def search_knn(self, query_reps: np.array, top_docs: int):
+        scores, indexes = self.search_arrays(query_reps, top_docs)
+        # reference indexer.py:212 (a -1 label indexes the last id there; kept identical)
+        id_arr = self.index_id_to_db_id
+        top_doc_ids = [[id_arr[idx] for idx in per_query_indexes] for per_query_indexes in indexes.tolist()]
+        return top_doc_ids, scores
+
+    def get_index_name(self):
+        return "flat_index"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# sparse: index build + retrieval
+# ------------------------------------------------------------------------------------------------------------------
+
+class SparseIndexer:
+    def __init__(self, model, index_dir, device, compute_stats=False, dim_voc=None, force_new=True,
+                 filename="array_index.h5py", **kwargs):
+        self.model = model
+        self.model.eval()
+        self.index_dir = index_dir
+        self.device = device
+        self._cuda = _cuda_device(device)
+        self.sparse_index = IndexDictOfArray(self.index_dir, dim_voc=dim_voc, force_new=force_new, filename=filename,
+                                             device=self._cuda)
+        self.compute_stats = compute_stats
+        if self.compute_stats:
+            self.l0 = L0()
+        self.model.to(self._cuda)
+        self.local_rank = self.device
+        # the reference asserts device == dist.get_rank() (indexer.py:235); without a process group rank is 0 / world 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            assert self.local_rank == torch.distributed.get_rank(), (self.local_rank, torch.distributed.get_rank())
+        self.rank = _rank()
+        self.world_size = _world_size()
+        print("world_size: {}, local_rank: {}".format(self.world_size, self.local_rank))
+
+    def index(self, collection_loader, id_dict=None):
+        dtype = torch.bfloat16 if supports_bfloat16() else torch.float32
+        print("Using bfloat16" if dtype == torch.bfloat16 else "Using float32")
+        doc_ids = {}
+        stats = defaultdict(float)
+        count = 0
+        with torch.inference_mode():
+            for t, batch in enumerate(tqdm(collection_loader, disable=not is_first_worker())):
+                inputs = {k: v.to(self._cuda) for k, v in batch.items() if k not in {"ids"}}
+                with torch.amp.autocast("cuda", dtype=dtype):
+                    batch_documents = self.model.encode(**inputs)   # [bz, vocab_size]
+                if self.compute_stats:
+                    stats["L0_d"] += self.l0(batch_documents).item()
+                row, col = torch.nonzero(batch_documents, as_tuple=True)   # row-major: row asc, col asc
+                data = batch_documents[row, col]
+                g_row = (row + count) * self.world_size + self.rank         # indexer.py:261-262, kept on the device
+                if isinstance(batch["ids"], torch.Tensor):
+                    batch_ids = to_list(batch["ids"])
+                else:
+                    assert isinstance(batch["ids"], list)
+                    batch_ids = batch["ids"]
+                if id_dict:
+                    batch_ids = [id_dict[x] for x in batch_ids]
+                present = torch.zeros(len(batch_ids), dtype=torch.bool, device=row.device)
+                present[row] = True
+                if bool(present.all()):
+                    base = count * self.world_size + self.rank
+                    doc_ids.update({base + i * self.world_size: y for i, y in enumerate(batch_ids)})
+                else:   # docs without any posting get no doc_ids entry (indexer.py:273-283)
+                    for i in torch.nonzero(present).flatten().tolist():
+                        doc_ids[(count + i) * self.world_size + self.rank] = batch_ids[i]
+                self.sparse_index.add_batch_document(g_row, col, data.float(), n_docs=len(batch_ids))
+                count += len(batch_ids)
+
+        if self.compute_stats:
+            stats = {key: value / len(collection_loader) for key, value in stats.items()}
+        if self.index_dir is not None:
+            self.sparse_index.save()
+            pickle.dump(doc_ids, open(os.path.join(self.index_dir, "doc_ids.pkl"), "wb"))
+            print("done iterating over the corpus...")
+            print("index contains {} posting lists".format(len(self.sparse_index)))
+            print("index contains {} documents".format(len(doc_ids)))
+            if self.compute_stats:
+                with open(os.path.join(self.index_dir, "index_stats.json"), "w") as handler:
+                    json.dump(stats, handler)
+        else:
+            self.sparse_index.finalize()
+            out = {"index": self.sparse_index, "ids_mapping": doc_ids}
+            if self.compute_stats:
+                out["stats"] = stats
+            return out
+
+
+def pack_queries(sparse_query_vecs):
+    """list of (col int32[nnz], values fp32[nnz]) (indexer.py:400-401) -> CSR-packed host arrays."""
+    q_offsets = np.zeros(len(sparse_query_vecs) + 1, dtype=np.int32)
+    if sparse_query_vecs:
+        q_offsets[1:] = np.cumsum([len(c) for c, _ in sparse_query_vecs])
+        q_terms = np.concatenate([np.asarray(c, dtype=np.int32) for c, _ in sparse_query_vecs]) if q_offsets[-1] else np.zeros(0, np.int32)
+        q_weights = np.concatenate([np.asarray(v, dtype=np.float32) for _, v in sparse_query_vecs]) if q_offsets[-1] else np.zeros(0, np.float32)
+    else:
+        q_terms, q_weights = np.zeros(0, np.int32), np.zeros(0, np.float32)
+    return q_offsets, q_terms.astype(np.int32, copy=False), q_weights.astype(np.float32, copy=False)
+
+
+class SparseRetrieval:
+    """retrieval from SparseIndexing (reference indexer.py:311-540), scored on the GPU."""
+
+    @staticmethod
+    def select_topk(filtered_indexes, scores, k):
+        """Reference semantics (indexer.py:315-322): `scores` are NEGATED; returns the k best rows, scores positive.
+        Host-side convenience kept for API parity; the retrieval path selects inside the search kernel."""
+        if len(filtered_indexes) > k:
+            sorted_ = np.argpartition(scores, k)[:k]
+            filtered_indexes, scores = filtered_indexes[sorted_], -scores[sorted_]
+        else:
+            scores = -scores
+        return filtered_indexes, scores
+
+    def __init__(self, model, config, dim_voc, device, dataset_name=None, index_d=None, compute_stats=False, is_beir=False,
+                 **kwargs):
+        self.model = model
+        self.model.eval()
+        self.device = device
+        self._cuda = _cuda_device(device)
+        assert ("index_dir" in config and index_d is None) or ("index_dir" not in config and index_d is not None)
+        if "index_dir" in config:
+            self.sparse_index = IndexDictOfArray(config["index_dir"], dim_voc=dim_voc, device=self._cuda)
+            self.doc_ids = pickle.load(open(os.path.join(config["index_dir"], "doc_ids.pkl"), "rb"))
+        else:
+            self.sparse_index = index_d["index"]
+            self.doc_ids = index_d["ids_mapping"]
+            self.sparse_index.fill_missing_terms(dim_voc)   # indexer.py:359-363
+        self.dim_voc = dim_voc
+        self.size_collection = self.sparse_index.nb_docs()
+
+        # The index moves to HBM once, for the lifetime of the retriever (replaces the numba.typed.Dict copy, :365-370).
+        with torch.cuda.device(self._cuda):
+            self.sparse_index.device = self._cuda
+            full = self.sparse_index.device_index()
+            self.shard_plan = shard.ShardPlan(self.size_collection, _world_size())
+            if self.shard_plan.world_size > 1:
+                lo, hi = self.shard_plan.bounds(_rank())
+                off, ids, w = shard.shard_sparse_csr(full.term_offsets, full.doc_ids, full.weights, lo, hi)
+                self.device_index = ops.SparseDeviceIndex.from_csr(off, ids, w, hi - lo)
+                self.doc_id_base = lo
+            else:
+                self.device_index = full
+                self.doc_id_base = 0
+
+        self.out_dir = os.path.join(config["out_dir"], dataset_name) if (dataset_name is not None and not is_beir) \
+            else config["out_dir"]
+        self.doc_stats = index_d["stats"] if (index_d is not None and compute_stats) else None
+        self.compute_stats = compute_stats
+        if self.compute_stats:
+            self.l0 = L0()
+        self.model.to(self._cuda)
+        self._ext_ids = None
+
+    def _generate_query_vecs(self, q_loader):
+        sparse_query_vecs = []
+        qids = []
+        with torch.inference_mode():
+            for t, batch in enumerate(tqdm(q_loader, total=len(q_loader), desc="generate query vecs",
+                                           disable=not is_first_worker())):
+                inputs = {k: v.to(self._cuda) for k, v in batch.items() if k not in {"ids"}}
+                with torch.amp.autocast("cuda", dtype=torch.bfloat16 if supports_bfloat16() else torch.float32):
+                    batch_sparse_reps = self.model.encode(**inputs)
+                qids.extend(batch["ids"] if isinstance(batch["ids"], list) else to_list(batch["ids"]))
+                # one nonzero for the whole batch instead of one per query (indexer.py:394-401): same (col, value) lists
+                row, col = torch.nonzero(batch_sparse_reps, as_tuple=True)
+                data = batch_sparse_reps[row, col].float().cpu().numpy().astype(np.float32)
+                counts = torch.bincount(row, minlength=batch_sparse_reps.shape[0]).cpu().numpy()
+                col = col.cpu().numpy().astype(np.int32)
+                bounds = np.concatenate([[0], np.cumsum(counts)])
+                for i in range(len(counts)):
+                    sparse_query_vecs.append((col[bounds[i]:bounds[i + 1]], data[bounds[i]:bounds[i + 1]]))
+        return sparse_query_vecs, qids
+
+    # ---- the hot path -----------------------------------------------------------------------------------------
+    def search_arrays(self, q_offsets, q_terms, q_weights, topk, threshold=0.0):
+        """HOST query arrays -> HOST result arrays (scores fp32 [Q,k], row ids int64 [Q,k], counts int32 [Q]).
+        Copies through pinned memory; this is the call bench.py times end to end."""
+        dev = self._cuda
+        with torch.cuda.device(dev):
+            d_off = torch.from_numpy(np.ascontiguousarray(q_offsets, dtype=np.int32)).pin_memory().to(dev, non_blocking=True)
+            d_terms = torch.from_numpy(np.ascontiguousarray(q_terms, dtype=np.int32)).pin_memory().to(dev, non_blocking=True)
+            d_w = torch.from_numpy(np.ascontiguousarray(q_weights, dtype=np.float32)).pin_memory().to(dev, non_blocking=True)
+            scores, ids, counts = ops.sparse_search(self.device_index, d_off, d_terms, d_w, int(topk), float(threshold),
+                                                    doc_id_base=self.doc_id_base)
+            if self.shard_plan.world_size > 1:
+                scores, ids, counts = shard.merge_shards(scores, ids, int(topk))
+            return scores.cpu().numpy(), ids.cpu().numpy(), counts.cpu().numpy()
+
+    def score_float(self, indexes_to_retrieve, query_values, threshold):
+        """API analogue of the reference's numba_score_float (indexer.py:324-344) for ONE query, on the GPU:
+        returns (filtered_indexes int64[h], -scores[filtered] fp32[h])."""
+        dev = self._cuda
+        with torch.cuda.device(dev):
+            off = torch.tensor([0, len(indexes_to_retrieve)], dtype=torch.int32, device=dev)
+            t = torch.as_tensor(np.asarray(indexes_to_retrieve, dtype=np.int32)).to(dev)
+            w = torch.as_tensor(np.asarray(query_values, dtype=np.float32)).to(dev)
+            scores = ops.sparse_scores(self.device_index, off, t, w)[0]
+            filtered = torch.nonzero(scores > threshold).flatten()
+            return (filtered + self.doc_id_base).cpu().numpy(), (-scores[filtered]).cpu().numpy()
+
+    def _external_ids(self):
+        if self._ext_ids is None:
+            ext = np.empty(self.size_collection, dtype=object)
+            if isinstance(self.doc_ids, dict):
+                for k, v in self.doc_ids.items():
+                    ext[k] = v
+            else:
+                ext[:len(self.doc_ids)] = self.doc_ids
+            self._ext_ids = ext
+        return self._ext_ids
+
+    def _sparse_retrieve_multithreaded(self, sparse_query_vecs, qids, threshold=0., topk=1000):
+        """Same contract as the reference (indexer.py:405-474): returns (res, stats) with
+        res[str(qid)][str(doc_ids[row])] = float(score); queries without an eligible doc get no key.  The 4-thread
+        numba loop is replaced by one batched GPU search over all queries."""
+        q_offsets, q_terms, q_weights = pack_queries(sparse_query_vecs)
+        scores, ids, counts = self.search_arrays(q_offsets, q_terms, q_weights, topk, threshold)
+        ext = self._external_ids()
+        res = defaultdict(dict)
+        stats = defaultdict(float)
+        for i, qid in enumerate(qids):
+            c = int(counts[i])
+            if c:
+                res[str(qid)].update(zip(map(str, ext[ids[i, :c]].tolist()), scores[i, :c].astype(float).tolist()))
+            stats["L0_q"] += (q_offsets[i + 1] - q_offsets[i]) / len(qids)
+        return res, stats
+
+    def retrieve(self, q_loader, topk, threshold=0.):
+        sparse_query_vecs, qids = self._generate_query_vecs(q_loader)
+        res, stats = self._sparse_retrieve_multithreaded(sparse_query_vecs, qids, threshold=threshold, topk=topk)
+        if is_first_worker():
+            if self.compute_stats:
+                with open(os.path.join(self.out_dir, "q_stats.json"), "w") as handler:
+                    json.dump(stats, handler)
+            with open(os.path.join(self.out_dir, "run.json"), "w") as handler:
+                json.dump(res, handler)
+        return res

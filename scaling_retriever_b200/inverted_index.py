@@ -1,0 +1,330 @@
+"""GPU-backed inverted-index container with the reference's IndexDictOfArray interface.
+
+Mirrors scaling_retriever/utils/inverted_index.py of the reference (class IndexDictOfArray :15-105, merge_indexes
+:108-170): same constructor arguments, attributes (`index_doc_id`, `index_doc_value`, `n`), methods
+(`add_batch_document`, `__len__`, `nb_docs`, `save`) and on-disk artefacts.  What changes is where the work is done:
+
+* add_batch_document (reference: one CPython list append per posting, :74-76) only logs the COO batch — on the
+  GPU if the batch arrives as CUDA tensors, so SparseIndexer.index never synchronises per batch;
+* the per-term arrays are produced by ONE stable GPU radix sort of the log (ops.csr_build), bit-exact with what the
+  appends would have built; `index_doc_id[t]` / `index_doc_value[t]` are numpy views into that CSR;
+* save() writes a native CSR bundle (three .npy files) next to the reference's files and, when h5py is importable,
+  also the reference's HDF5 layout (`dim`, `index_doc_id_{t}`, `index_doc_value_{t}`); the loader reads either.
+
+There is no CPU build path: finalising an index without a CUDA device raises.
+"""
+import json
+import os
+import pickle
+from collections.abc import Mapping
+
+import numpy as np
+import torch
+
+from . import ops
+
+CSR_FILES = ("csr_term_offsets.npy", "csr_doc_ids.npy", "csr_weights.npy")
+
+
+class _TermArrays(Mapping):
+    """dict[int -> ndarray] view over CSR arrays (what the reference stores as a real dict of arrays)."""
+
+    def __init__(self, term_offsets, data, keys):
+        self._off = term_offsets
+        self._data = data
+        self._keys = keys            # term ids exposed as dict keys (ascending)
+        self._keyset = None
+
+    def __getitem__(self, key):
+        key = int(key)
+        if key < 0 or key >= len(self._off) - 1 or (self._keyset is not None and key not in self._keyset):
+            raise KeyError(key)
+        return self._data[self._off[key]:self._off[key + 1]]
+
+    def __contains__(self, key):
+        if self._keyset is None:
+            self._keyset = set(int(k) for k in self._keys)
+        try:
+            return int(key) in self._keyset
+        except (TypeError, ValueError):
+            return False
+
+    def __iter__(self):
+        return iter(int(k) for k in self._keys)
+
+    def __len__(self):
+        return len(self._keys)
+
+
+def _as_device_i32(x, device):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.int32, non_blocking=True).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x).astype(np.int32, copy=False)).to(device, non_blocking=True)
+
+
+def _as_device_f32(x, device):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x).astype(np.float32, copy=False)).to(device, non_blocking=True)
+
+
+class IndexDictOfArray:
+    def __init__(self, index_path=None, force_new=False, filename="array_index.h5py", dim_voc=None, device=None):
+        self.dim_voc = dim_voc
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None and torch.cuda.is_available() \
+            else (torch.device(device) if device is not None else None)
+        self._log = []              # COO batches (rows, cols, vals) as device tensors, in feed order
+        self._csr_host = None       # (term_offsets, doc_ids, weights) numpy
+        self._csr_dev = None        # same as CUDA tensors
+        self._views = None
+        self._all_keys = False      # loaded indexes expose every term id in range(dim) like the reference loader
+        self.n = 0
+        if index_path is not None:
+            self.index_path = index_path
+            if not os.path.exists(index_path):
+                os.makedirs(index_path)
+            self.filename = os.path.join(self.index_path, filename)
+            if self._exists_on_disk() and not force_new:
+                print("index already exists, loading...")
+                self._load(dim_voc)
+                print("done loading index...")
+                doc_ids = pickle.load(open(os.path.join(self.index_path, "doc_ids.pkl"), "rb"))
+                if isinstance(doc_ids, list):
+                    self.n = len(doc_ids)
+                else:   # dict row id -> external id; the reference takes max key + 1 (inverted_index.py:47-55)
+                    keys = np.fromiter(doc_ids.keys(), dtype=np.int64, count=len(doc_ids))
+                    print("min_val: ", keys.min(), "max_val: ", keys.max())
+                    assert keys.min() == 0, keys.min()
+                    self.n = int(keys.max()) + 1
+            else:
+                print("initializing new index...")
+        else:
+            print("initializing new index...")
+
+    # ---- disk -----------------------------------------------------------------------------------------------
+    def _csr_paths(self):
+        return [os.path.join(self.index_path, f) for f in CSR_FILES]
+
+    def _exists_on_disk(self):
+        return all(os.path.exists(p) for p in self._csr_paths()) or os.path.exists(self.filename)
+
+    def _load(self, dim_voc):
+        if all(os.path.exists(p) for p in self._csr_paths()):
+            off, ids, w = (np.load(p) for p in self._csr_paths())
+            if dim_voc is not None and dim_voc != len(off) - 1:   # the reference trusts dim_voc (inverted_index.py:25-26)
+                off = _resize_offsets(off, dim_voc)
+        else:
+            off, ids, w = _load_hdf5(self.filename, dim_voc)
+        self._set_csr_host(off.astype(np.int64), ids.astype(np.int32), w.astype(np.float32))
+        self._all_keys = True
+
+    def _set_csr_host(self, off, ids, w):
+        self._csr_host = (off, ids, w)
+        self._csr_dev = None
+        self._views = None
+        self.dim_voc = len(off) - 1
+
+    # ---- build ----------------------------------------------------------------------------------------------
+    def add_batch_document(self, row, col, data, n_docs=-1):
+        """add a batch of documents to the index (reference inverted_index.py:67-76): logged, sorted later."""
+        if self._csr_host is not None or self._csr_dev is not None:
+            raise RuntimeError("add_batch_document after the index was finalised/loaded is not supported")
+        if self.device is None or self.device.type != "cuda":
+            raise RuntimeError("IndexDictOfArray needs a CUDA device to build an index (no CPU fallback)")
+        r = _as_device_i32(row, self.device)
+        c = _as_device_i32(col, self.device)
+        v = _as_device_f32(data, self.device)
+        if n_docs < 0:
+            self.n += int(torch.unique(r).numel())
+        else:
+            self.n += n_docs
+        self._log.append((r, c, v))
+
+    def _n_terms_for_build(self):
+        if self.dim_voc is not None:
+            return int(self.dim_voc)
+        mx = max((int(c.max().item()) for _, c, _ in self._log if c.numel()), default=-1)
+        return mx + 1 if mx >= 0 else 1
+
+    def finalize(self):
+        """Run the GPU CSR build over the logged batches (idempotent). Returns device (term_offsets, doc_ids, weights)."""
+        if self._csr_dev is not None:
+            return self._csr_dev
+        if self._csr_host is not None:
+            dev = self.device if self.device is not None else torch.device("cuda", torch.cuda.current_device())
+            self._csr_dev = tuple(torch.as_tensor(a).to(dev) for a in self._csr_host)
+            return self._csr_dev
+        if self.device is None or self.device.type != "cuda":
+            raise RuntimeError("IndexDictOfArray needs a CUDA device to build an index (no CPU fallback)")
+        n_terms = self._n_terms_for_build()
+        if self._log:
+            rows = torch.cat([r for r, _, _ in self._log])
+            cols = torch.cat([c for _, c, _ in self._log])
+            vals = torch.cat([v for _, _, v in self._log])
+        else:
+            rows = torch.empty(0, dtype=torch.int32, device=self.device)
+            cols = rows.clone()
+            vals = torch.empty(0, dtype=torch.float32, device=self.device)
+        self._log = []
+        n_docs = max(self.n, int(rows.max().item()) + 1 if rows.numel() else 0)
+        self._csr_dev = ops.csr_build(rows, cols, vals, n_terms, n_docs, sort_docs=False)
+        self.dim_voc = n_terms
+        return self._csr_dev
+
+    def csr_host(self):
+        if self._csr_host is None:
+            off, ids, w = self.finalize()
+            self._csr_host = (off.cpu().numpy(), ids.cpu().numpy(), w.cpu().numpy())
+        return self._csr_host
+
+    def _make_views(self):
+        if self._views is None:
+            off, ids, w = self.csr_host()
+            keys = np.arange(len(off) - 1) if self._all_keys else np.nonzero(np.diff(off))[0]
+            self._views = (_TermArrays(off, ids, keys), _TermArrays(off, w, keys))
+        return self._views
+
+    @property
+    def index_doc_id(self):
+        return self._make_views()[0]
+
+    @property
+    def index_doc_value(self):
+        return self._make_views()[1]
+
+    def fill_missing_terms(self, dim_voc):
+        """SparseRetrieval.__init__ fills absent posting lists with empty arrays (indexer.py:359-363)."""
+        off, ids, w = self.csr_host()
+        if dim_voc != len(off) - 1:
+            self._set_csr_host(_resize_offsets(off, dim_voc), ids, w)
+        self._all_keys = True
+        self._views = None
+
+    def __len__(self):
+        return len(self.index_doc_id)
+
+    def nb_docs(self):
+        return self.n
+
+    def save(self, dim=None):
+        print("converting to numpy")
+        off, ids, w = self.csr_host()
+        print("save to disk")
+        print("filename: ", self.filename)
+        for path, arr in zip(self._csr_paths(), (off, ids, w)):
+            np.save(path, arr)
+        keys = np.nonzero(np.diff(off))[0]
+        try:
+            import h5py  # optional: the reference's HDF5 layout (inverted_index.py:92-100)
+        except ImportError:
+            h5py = None
+        if h5py is not None:
+            with h5py.File(self.filename, "w") as f:
+                f.create_dataset("dim", data=int(dim) if dim else len(keys))
+                for key in keys:
+                    f.create_dataset("index_doc_id_{}".format(key), data=ids[off[key]:off[key + 1]])
+                    f.create_dataset("index_doc_value_{}".format(key), data=w[off[key]:off[key + 1]])
+        print("saving index distribution...")
+        index_dist = {int(k): int(off[k + 1] - off[k]) for k in keys}
+        json.dump(index_dist, open(os.path.join(self.index_path, "index_dist.json"), "w"))
+
+    # ---- search-side view -----------------------------------------------------------------------------------
+    def device_index(self):
+        """Doc-sorted CSR + doc-block skip table on the GPU (what SparseRetrieval searches)."""
+        off, ids, w = self.finalize()
+        n_docs = int(self.n)
+        try:
+            return ops.SparseDeviceIndex.from_csr(off, ids, w, n_docs)
+        except Exception as exc:   # lists not ascending (merged multi-rank index): re-sort by (term, doc) on the GPU
+            from ._lib import B200RetError
+            if not (isinstance(exc, B200RetError) and exc.code == -4):
+                raise
+        counts = (off[1:] - off[:-1])
+        cols = torch.repeat_interleave(torch.arange(off.numel() - 1, dtype=torch.int32, device=off.device), counts,
+                                       output_size=ids.numel())
+        return ops.SparseDeviceIndex.from_coo(ids, cols, w, off.numel() - 1, n_docs)
+
+
+def _resize_offsets(off, dim_voc):
+    n = len(off) - 1
+    if dim_voc > n:
+        return np.concatenate([off, np.full(dim_voc - n, off[-1], dtype=off.dtype)])
+    if off[dim_voc] != off[-1]:
+        raise ValueError(f"dim_voc={dim_voc} would drop non-empty posting lists (index has {n} terms)")
+    return off[:dim_voc + 1].copy()
+
+
+def _load_hdf5(filename, dim_voc):
+    """The reference loader (inverted_index.py:24-41): iterate range(dim), missing datasets -> empty lists."""
+    try:
+        import h5py
+    except ImportError as exc:
+        raise ImportError(f"{filename} is an HDF5 index and h5py is not installed; re-save it as the native CSR bundle "
+                          f"({', '.join(CSR_FILES)}) on a machine with h5py") from exc
+    with h5py.File(filename, "r") as f:
+        dim = dim_voc if dim_voc is not None else int(f["dim"][()])
+        off = np.zeros(dim + 1, dtype=np.int64)
+        ids, vals = [], []
+        for key in range(dim):
+            name = "index_doc_id_{}".format(key)
+            if name in f:
+                a = np.array(f[name], dtype=np.int32)
+                v = np.array(f["index_doc_value_{}".format(key)], dtype=np.float32)
+                ids.append(a)
+                vals.append(v)
+                off[key + 1] = off[key] + len(a)
+            else:
+                off[key + 1] = off[key]
+    ids = np.concatenate(ids) if ids else np.array([], dtype=np.int32)
+    vals = np.concatenate(vals) if vals else np.array([], dtype=np.float32)
+    return off, ids, vals
+
+
+def merge_indexes(model_name_or_path, filename="array_index.h5py", index_name="index", index_dir=None):
+    """Merge per-rank index dirs `index_0`, `index_1`, ... into `index` (reference inverted_index.py:108-170):
+    per term, the posting arrays of the shards are appended in directory order; doc_ids maps are unioned;
+    L0_d is averaged.  Here the append is one stable GPU sort of the concatenated shard postings by term."""
+    with open(os.path.join(model_name_or_path, "config.json")) as fin:
+        config = json.load(fin)
+    dim_voc = config["vocab_size"]
+    print("dim_voc: ", dim_voc)
+    root = index_dir if index_dir is not None else model_name_or_path
+    index_dirs = [os.path.join(root, d) for d in os.listdir(root) if d.startswith(index_name)]
+    assert len(index_dirs) in [1, 2, 4], index_dirs
+    if len(index_dirs) == 1:
+        print("only one index, no need to merge")
+        return
+    rows, cols, vals = [], [], []
+    doc_ids, index_dist, index_stats = dict(), {}, {"L0_d": 0}
+    for idx_dir in index_dirs:
+        shard = IndexDictOfArray(idx_dir, filename=filename, dim_voc=dim_voc)
+        off, ids, w = shard.csr_host()
+        cols.append(np.repeat(np.arange(dim_voc, dtype=np.int32), np.diff(off)))
+        rows.append(ids)
+        vals.append(w)
+        with open(os.path.join(idx_dir, "doc_ids.pkl"), "rb") as f:
+            doc_ids.update(pickle.load(f))
+        with open(os.path.join(idx_dir, "index_dist.json"), "r") as f:
+            index_dist.update(json.load(f))
+        with open(os.path.join(idx_dir, "index_stats.json"), "r") as f:
+            index_stats["L0_d"] += json.load(f)["L0_d"] / len(index_dirs)
+    out_index_dir = os.path.join(root, index_name)
+    merged = IndexDictOfArray(out_index_dir, force_new=True, filename=filename, dim_voc=dim_voc)
+    merged.add_batch_document(np.concatenate(rows), np.concatenate(cols), np.concatenate(vals), n_docs=len(doc_ids))
+    merged.save(dim=dim_voc)
+    with open(os.path.join(out_index_dir, "doc_ids.pkl"), "wb") as f:
+        pickle.dump(doc_ids, f)
+    with open(os.path.join(out_index_dir, "index_dist.json"), "w") as f:
+        json.dump(index_dist, f)
+    with open(os.path.join(out_index_dir, "index_stats.json"), "w") as f:
+        json.dump(index_stats, f)
+
+
+if __name__ == "__main__":
+    import argparse
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--model_name_or_path", type=str, required=True)
+    parser.add_argument("--index_name", default="index", type=str)
+    parser.add_argument("--index_dir", default=None, type=str)
+    args = parser.parse_args()
+    merge_indexes(args.model_name_or_path, index_name=args.index_name, index_dir=args.index_dir)

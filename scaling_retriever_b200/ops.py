@@ -1,0 +1,205 @@
+"""Torch-tensor wrappers over the C ABI (include/b200ret.h).
+
+PyTorch is plumbing here: it owns device memory (caching allocator) and the current stream; the compute is
+the hand-written sm_100a kernels in csrc/.  Every wrapper validates device/dtype/contiguity and raises on
+CPU tensors — there is no CPU fallback.
+"""
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check_cuda(name, t, dtype):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: tensor is on {t.device}; the b200ret kernels need CUDA tensors (no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous")
+
+
+def block_docs():
+    """Documents per warp-private score tile compiled into the sparse search kernel."""
+    return int(_lib.load().b200ret_sparse_block_docs())
+
+
+def device_info():
+    import ctypes
+    sm, major, minor, smem = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_size_t()
+    _lib.check(_lib.load().b200ret_device_info(ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor), ctypes.byref(smem)))
+    return {"sm_count": sm.value, "cc": (major.value, minor.value), "smem_optin_bytes": smem.value}
+
+
+def csr_build(rows, cols, vals, n_terms, n_docs, sort_docs=False):
+    """COO postings in feed order -> (term_offsets int64[V+1], doc_ids int32[nnz], weights fp32[nnz]).
+
+    GPU replacement for IndexDictOfArray.add_batch_document + the ndarray conversion in save()
+    (reference scaling_retriever/utils/inverted_index.py:67-76, :84-88).
+    """
+    lib = _lib.load()
+    _check_cuda("rows", rows, torch.int32)
+    _check_cuda("cols", cols, torch.int32)
+    _check_cuda("vals", vals, torch.float32)
+    nnz = rows.numel()
+    if cols.numel() != nnz or vals.numel() != nnz:
+        raise ValueError("rows, cols, vals must have the same length")
+    dev = rows.device
+    with torch.cuda.device(dev):
+        term_offsets = torch.empty(n_terms + 1, dtype=torch.int64, device=dev)
+        doc_ids = torch.empty(nnz, dtype=torch.int32, device=dev)
+        weights = torch.empty(nnz, dtype=torch.float32, device=dev)
+        ws_bytes = lib.b200ret_csr_build_workspace_bytes(nnz, n_terms, n_docs, int(sort_docs))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.b200ret_csr_build(_ptr(rows), _ptr(cols), _ptr(vals), nnz, n_terms, n_docs, int(sort_docs),
+                                         _ptr(term_offsets), _ptr(doc_ids), _ptr(weights), _ptr(ws), ws_bytes, _stream()))
+    return term_offsets, doc_ids, weights
+
+
+def block_table_build(term_offsets, doc_ids, n_docs, blk_docs=None):
+    """Doc-block skip table (uint32 positions stored in an int32 tensor of shape [n_terms, n_blocks+1])."""
+    lib = _lib.load()
+    _check_cuda("term_offsets", term_offsets, torch.int64)
+    _check_cuda("doc_ids", doc_ids, torch.int32)
+    blk_docs = block_docs() if blk_docs is None else blk_docs
+    n_terms = term_offsets.numel() - 1
+    n_blocks = (n_docs + blk_docs - 1) // blk_docs
+    dev = term_offsets.device
+    with torch.cuda.device(dev):
+        table = torch.empty((n_terms, n_blocks + 1), dtype=torch.int32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.check(lib.b200ret_block_table_build(_ptr(term_offsets), _ptr(doc_ids), doc_ids.numel(), n_terms, n_docs, blk_docs,
+                                                 _ptr(table), _ptr(status), _stream()))
+    return table
+
+
+@dataclass
+class SparseDeviceIndex:
+    """A doc-sorted CSR posting-list index resident in HBM plus its doc-block skip table."""
+    term_offsets: torch.Tensor   # int64 [n_terms + 1]
+    doc_ids: torch.Tensor        # int32 [nnz], ascending inside each term
+    weights: torch.Tensor        # fp32 [nnz]
+    table: torch.Tensor          # int32 storage of uint32 [n_terms, n_blocks + 1]
+    n_terms: int
+    n_docs: int
+    block_docs: int
+
+    @property
+    def nnz(self):
+        return self.doc_ids.numel()
+
+    @property
+    def device(self):
+        return self.doc_ids.device
+
+    @classmethod
+    def from_csr(cls, term_offsets, doc_ids, weights, n_docs):
+        table = block_table_build(term_offsets, doc_ids, n_docs)
+        return cls(term_offsets, doc_ids, weights, table, term_offsets.numel() - 1, int(n_docs), block_docs())
+
+    @classmethod
+    def from_coo(cls, rows, cols, vals, n_terms, n_docs):
+        """Build from COO postings in any order (lists come out ascending in doc id)."""
+        term_offsets, doc_ids, weights = csr_build(rows, cols, vals, n_terms, n_docs, sort_docs=True)
+        return cls.from_csr(term_offsets, doc_ids, weights, n_docs)
+
+
+def sparse_search(index, q_offsets, q_terms, q_weights, k, threshold=0.0, doc_id_base=0):
+    """Score a CSR-packed query batch against `index`; return (scores fp32[Q,k], ids int64[Q,k], counts int32[Q]).
+
+    Rows are sorted by (score desc, doc id asc); slots past counts[q] hold (-inf, -1).
+    """
+    lib = _lib.load()
+    _check_cuda("q_offsets", q_offsets, torch.int32)
+    _check_cuda("q_terms", q_terms, torch.int32)
+    _check_cuda("q_weights", q_weights, torch.float32)
+    n_queries = q_offsets.numel() - 1
+    dev = index.device
+    with torch.cuda.device(dev):
+        out_scores = torch.empty((n_queries, k), dtype=torch.float32, device=dev)
+        out_ids = torch.empty((n_queries, k), dtype=torch.int64, device=dev)
+        out_counts = torch.empty(n_queries, dtype=torch.int32, device=dev)
+        ws_bytes = lib.b200ret_sparse_search_workspace_bytes(n_queries, k)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.b200ret_sparse_search(
+            _ptr(index.table), _ptr(index.doc_ids), _ptr(index.weights), index.n_terms, index.n_docs, index.block_docs,
+            _ptr(q_offsets), _ptr(q_terms), _ptr(q_weights), n_queries, k, float(threshold), int(doc_id_base),
+            _ptr(out_scores), _ptr(out_ids), _ptr(out_counts), _ptr(ws), ws_bytes, _stream()))
+    return out_scores, out_ids, out_counts
+
+
+def sparse_scores(index, q_offsets, q_terms, q_weights):
+    """Full fp32 score vectors [Q, n_docs] (the `scores` array of numba_score_float, indexer.py:332-341)."""
+    lib = _lib.load()
+    _check_cuda("q_offsets", q_offsets, torch.int32)
+    _check_cuda("q_terms", q_terms, torch.int32)
+    _check_cuda("q_weights", q_weights, torch.float32)
+    n_queries = q_offsets.numel() - 1
+    dev = index.device
+    n_blocks = (index.n_docs + index.block_docs - 1) // index.block_docs
+    with torch.cuda.device(dev):
+        out = torch.zeros((n_queries, n_blocks * index.block_docs), dtype=torch.float32, device=dev)
+        ws = torch.empty(256, dtype=torch.uint8, device=dev)
+        _lib.check(lib.b200ret_sparse_scores(
+            _ptr(index.table), _ptr(index.doc_ids), _ptr(index.weights), index.n_terms, index.n_docs, index.block_docs,
+            _ptr(q_offsets), _ptr(q_terms), _ptr(q_weights), n_queries, _ptr(out), _ptr(ws), 256, _stream()))
+    return out[:, :index.n_docs]
+
+
+def f32_to_bf16(src):
+    lib = _lib.load()
+    _check_cuda("src", src, torch.float32)
+    dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    with torch.cuda.device(src.device):
+        _lib.check(lib.b200ret_f32_to_bf16(_ptr(src), _ptr(dst), src.numel(), _stream()))
+    return dst
+
+
+def dense_search(corpus, queries, k, doc_id_base=0):
+    """Exact top-k of queries . corpus^T (bf16 inputs, fp32 accumulate); rows sorted descending."""
+    lib = _lib.load()
+    _check_cuda("corpus", corpus, torch.bfloat16)
+    _check_cuda("queries", queries, torch.bfloat16)
+    n_docs, dim = corpus.shape
+    n_queries = queries.shape[0]
+    if queries.shape[1] != dim:
+        raise ValueError(f"dim mismatch: corpus {dim}, queries {queries.shape[1]}")
+    dev = corpus.device
+    with torch.cuda.device(dev):
+        out_scores = torch.empty((n_queries, k), dtype=torch.float32, device=dev)
+        out_ids = torch.empty((n_queries, k), dtype=torch.int64, device=dev)
+        out_counts = torch.empty(n_queries, dtype=torch.int32, device=dev)
+        ws_bytes = lib.b200ret_dense_search_workspace_bytes(n_queries, n_docs, dim, k)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.b200ret_dense_search(_ptr(corpus), _ptr(queries), n_docs, n_queries, dim, k, int(doc_id_base),
+                                            _ptr(out_scores), _ptr(out_ids), _ptr(out_counts), _ptr(ws), ws_bytes, _stream()))
+    return out_scores, out_ids, out_counts
+
+
+def merge_topk(scores, ids, k):
+    """Merge per-shard rows [G, Q, k] into the global top-k [Q, k] (same total order as the search kernels)."""
+    lib = _lib.load()
+    _check_cuda("scores", scores, torch.float32)
+    _check_cuda("ids", ids, torch.int64)
+    n_shards, n_queries, kk = scores.shape
+    if kk != k or ids.shape != scores.shape:
+        raise ValueError("scores/ids must both be [n_shards, n_queries, k]")
+    dev = scores.device
+    with torch.cuda.device(dev):
+        out_scores = torch.empty((n_queries, k), dtype=torch.float32, device=dev)
+        out_ids = torch.empty((n_queries, k), dtype=torch.int64, device=dev)
+        out_counts = torch.empty(n_queries, dtype=torch.int32, device=dev)
+        _lib.check(lib.b200ret_merge_topk(_ptr(scores), _ptr(ids), n_shards, n_queries, k,
+                                          _ptr(out_scores), _ptr(out_ids), _ptr(out_counts), _stream()))
+    return out_scores, out_ids, out_counts

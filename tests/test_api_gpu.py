@@ -1,0 +1,180 @@
+"""Class-API parity on the GPU: the reference's call sequence (eval_sparse.py:104-106,149-151; eval_dense.py:188-241)
+driven through the drop-in `scaling_retriever` modules with a fake encoder, checked against the golden run produced
+by the reference's own SparseRetrieval._sparse_retrieve_multithreaded (tests/golden/retrieve_golden.json)."""
+import json
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dense_oracle, sparse_oracle
+from scaling_retriever.indexer import DenseFlatIndexer, SparseIndexer, SparseRetrieval, store_embs
+from scaling_retriever.utils.inverted_index import IndexDictOfArray
+from scaling_retriever.utils.utils import obtain_doc_vec_dir_files
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class FakeSparseEncoder(torch.nn.Module):
+    """Stands in for LlamaBiSparse: encode(input_ids=rows) returns pre-computed [bz, vocab] sparse vectors."""
+
+    def __init__(self, table):
+        super().__init__()
+        self.register_buffer("table", table)
+        self.vocab_size = table.shape[1]
+
+    def encode(self, input_ids):
+        return self.table[input_ids]
+
+
+class Loader(list):
+    batch_size = 64
+
+
+def make_loader(n, ids, bs=64):
+    return Loader({"input_ids": torch.arange(i, min(i + bs, n)), "ids": ids[i:i + bs]} for i in range(0, n, bs))
+
+
+def dense_from_csr(off, ids, vals, n_docs):
+    table = torch.zeros((n_docs, len(off) - 1), dtype=torch.float32)
+    cols = np.repeat(np.arange(len(off) - 1), np.diff(off))
+    table[torch.as_tensor(ids.astype(np.int64)), torch.as_tensor(cols)] = torch.as_tensor(vals)
+    return table
+
+
+@pytest.fixture(scope="module")
+def golden_run():
+    with open(os.path.join(HERE, "golden", "retrieve_golden.json")) as f:
+        return json.load(f)
+
+
+def check_run(res, golden_res, oracle_scores_by_qid, row_of):
+    assert set(res.keys()) == set(golden_res.keys())      # queries without hits have no key on either side
+    for qid, ref_docs in golden_res.items():
+        ours = res[qid]
+        assert len(ours) == len(ref_docs)
+        ref_sorted = sorted(ref_docs.values(), reverse=True)
+        assert sorted(ours.values(), reverse=True) == ref_sorted
+        kth = ref_sorted[-1]
+        assert {d for d, s in ours.items() if s > kth} == {d for d, s in ref_docs.items() if s > kth}
+        full = oracle_scores_by_qid[qid]
+        for d, s in ours.items():
+            assert float(full[row_of(d)]) == s
+
+
+@pytest.mark.parametrize("on_disk", [False, True])
+def test_sparse_index_then_retrieve_matches_reference_run(golden, golden_run, cuda, tmp_path, on_disk):
+    off, ids, vals = golden["C_offsets"], golden["C_ids"], golden["C_vals"]
+    n_docs, n_terms = int(golden["C_n_docs"]), int(golden["C_n_terms"])
+    doc_table = dense_from_csr(off, ids, vals, n_docs)
+    ext_ids = [f"D{7 * i}" for i in range(n_docs)]
+    index_dir = str(tmp_path / "index") if on_disk else None
+    out_dir = str(tmp_path / "out")
+    os.makedirs(out_dir)
+
+    indexer = SparseIndexer(FakeSparseEncoder(doc_table), index_dir=index_dir, device=0, compute_stats=True, dim_voc=n_terms)
+    out = indexer.index(make_loader(n_docs, ext_ids))
+    if on_disk:
+        assert out is None
+        for f in ("doc_ids.pkl", "index_dist.json", "index_stats.json", "csr_doc_ids.npy"):
+            assert os.path.exists(os.path.join(index_dir, f)), f
+        assert pickle.load(open(os.path.join(index_dir, "doc_ids.pkl"), "rb"))[3] == "D21"
+        loaded = IndexDictOfArray(index_dir, dim_voc=n_terms)
+        assert loaded.nb_docs() == n_docs
+        for t in (0, 5, n_terms - 1):
+            assert np.array_equal(loaded.index_doc_id[t], ids[off[t]:off[t + 1]])
+            assert np.array_equal(loaded.index_doc_value[t], vals[off[t]:off[t + 1]])
+        retriever = SparseRetrieval(FakeSparseEncoder(doc_table), {"index_dir": index_dir, "out_dir": out_dir}, n_terms, 0,
+                                    compute_stats=True)
+    else:
+        assert set(out) == {"index", "ids_mapping", "stats"}
+        assert abs(out["stats"]["L0_d"] - len(ids) / n_docs) < 0.5
+        # the in-memory index exposes the reference's dict-of-arrays view, bit-exact with the reference build
+        for t in np.nonzero(np.diff(off))[0][:20]:
+            assert np.array_equal(out["index"].index_doc_id[int(t)], ids[off[t]:off[t + 1]])
+            assert np.array_equal(out["index"].index_doc_value[int(t)], vals[off[t]:off[t + 1]])
+        retriever = SparseRetrieval(FakeSparseEncoder(doc_table), {"out_dir": out_dir}, n_terms, 0, index_d=out, compute_stats=True)
+
+    q_off, q_t, q_w = golden["C_q_offsets"], golden["C_q_terms"], golden["C_q_weights"]
+    nq = len(q_off) - 1
+    q_table = torch.zeros((nq, n_terms))
+    for i in range(nq):
+        q_table[i, torch.as_tensor(q_t[q_off[i]:q_off[i + 1]].astype(np.int64))] = torch.as_tensor(q_w[q_off[i]:q_off[i + 1]])
+    retriever.model = FakeSparseEncoder(q_table).to(cuda)
+    res = retriever.retrieve(make_loader(nq, golden_run["qids"], bs=5), topk=golden_run["topk"], threshold=golden_run["threshold"])
+
+    index_ids, index_vals = sparse_oracle.csr_to_dicts(off, ids, vals, n_terms)
+    full = {}
+    for i, qid in enumerate(golden_run["qids"]):
+        sc = np.zeros(n_docs, dtype=np.float32)
+        f, neg = sparse_oracle.score_float(index_ids, index_vals, q_t[q_off[i]:q_off[i + 1]], q_w[q_off[i]:q_off[i + 1]], 0.0, n_docs)
+        sc[f] = -neg
+        full[str(qid)] = sc
+    check_run(res, golden_run["res"], full, lambda d: int(d[1:]) // 7)
+    with open(os.path.join(out_dir, "run.json")) as f:
+        assert json.load(f) == json.loads(json.dumps(res))
+    with open(os.path.join(out_dir, "q_stats.json")) as f:
+        assert abs(json.load(f)["L0_q"] - golden_run["stats"]["L0_q"]) < 1e-9
+
+
+def test_score_float_matches_reference_golden(golden, cuda, tmp_path):
+    off, ids, vals = golden["C_offsets"], golden["C_ids"], golden["C_vals"]
+    n_docs, n_terms = int(golden["C_n_docs"]), int(golden["C_n_terms"])
+    index = IndexDictOfArray(index_path=None, dim_voc=n_terms)
+    index.add_batch_document(ids, np.repeat(np.arange(n_terms), np.diff(off)), vals, n_docs=n_docs)
+    retriever = SparseRetrieval(torch.nn.Linear(1, 1), {"out_dir": str(tmp_path)}, n_terms, 0,
+                                index_d={"index": index, "ids_mapping": {i: i for i in range(n_docs)}})
+    q_off, q_t, q_w = golden["C_q_offsets"], golden["C_q_terms"], golden["C_q_weights"]
+    for qi in (0, 3, 9, 11):
+        f, neg = retriever.score_float(q_t[q_off[qi]:q_off[qi + 1]], q_w[q_off[qi]:q_off[qi + 1]], threshold=1.0)
+        assert np.array_equal(f, golden[f"C_t1_q{qi}_filtered"])
+        assert np.array_equal(neg.view(np.uint32), golden[f"C_t1_q{qi}_neg_scores"].view(np.uint32))
+
+
+class FakeDenseEncoder(torch.nn.Module):
+    def __init__(self, table):
+        super().__init__()
+        self.register_buffer("table", table)
+        self.hidden_size = table.shape[1]
+
+    def doc_encode(self, input_ids):
+        return self.table[input_ids]
+
+
+def test_dense_store_embs_then_search_knn(cuda, tmp_path):
+    """eval_dense.py's sequence: store_embs -> plan.json/npy shards -> index_data -> search_knn, vs the fp32 restatement
+    of IndexFlatIP run on the bf16-rounded inputs (ids identical up to near-ties, scores <= 1e-2 rel per the spec)."""
+    n, d, nq, k = 5000, 128, 37, 100
+    g = torch.Generator().manual_seed(0)
+    docs = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=1)
+    queries = torch.nn.functional.normalize(torch.randn(nq, d, generator=g), dim=1)
+    ext_ids = [f"P{i}" for i in range(n)]
+    embed_dir = str(tmp_path / "embs")
+    os.makedirs(embed_dir)
+    store_embs(FakeDenseEncoder(docs).to(cuda), make_loader(n, ext_ids), local_rank=0, index_dir=embed_dir, device=cuda,
+               chunk_size=64 * 30)
+    vec_files, id_files = obtain_doc_vec_dir_files(embed_dir)
+    assert len(vec_files) == 3
+    doc_reps = np.concatenate([np.load(f) for f in vec_files], axis=0)
+    doc_ids = np.concatenate([np.load(f) for f in id_files]).tolist()
+    assert doc_reps.shape == (n, d) and doc_ids == ext_ids
+
+    index = DenseFlatIndexer()
+    index.init_index(d)
+    index.index_data(doc_reps, doc_ids)
+    top_ids, top_scores = index.search_knn(queries.numpy(), k)
+    assert top_scores.shape == (nq, k) and top_scores.dtype == np.float32 and len(top_ids) == nq and len(top_ids[0]) == k
+    assert np.all(np.diff(top_scores, axis=1) <= 0)
+
+    docs16 = torch.as_tensor(doc_reps).bfloat16().float().numpy()
+    q16 = queries.bfloat16().float().numpy()
+    o_ids, o_scores = dense_oracle.search_knn(docs16, doc_ids, q16, k)
+    np.testing.assert_allclose(top_scores, o_scores, rtol=1e-4, atol=1e-6)
+    exact = dense_oracle.flat_ip_search(doc_reps, queries.numpy(), k)[0]
+    np.testing.assert_allclose(top_scores, exact, rtol=1e-2, atol=1e-3)
+    for a, b, s in zip(top_ids, o_ids, o_scores):
+        assert len(set(a) & set(b)) >= k - 2          # near-ties at the k boundary may swap
+        assert a[0] == b[0] or abs(s[0] - s[1]) < 1e-5

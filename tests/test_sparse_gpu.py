@@ -1,0 +1,238 @@
+"""GPU parity tests of the sparse path: every check calls the CUDA kernels through the C ABI (ops.* -> ctypes ->
+libb200ret.so) and compares with (a) golden vectors produced by the reference's own code (tests/golden) and (b) the
+CPU oracle (oracle/) on the same seeded inputs.  Integer/index work is compared bit-exactly; fp32 scores are
+compared bit-exactly too (same multiply/add order as the reference), which is stricter than the 1e-5 the spec allows.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle, sparse_oracle
+from scaling_retriever_b200 import ops, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def dev_i32(a, cuda):
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(cuda)
+
+
+def dev_f32(a, cuda):
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(cuda)
+
+
+def build_index(off, ids, vals, n_docs, cuda):
+    return ops.SparseDeviceIndex.from_csr(torch.as_tensor(off).to(cuda), dev_i32(ids, cuda), dev_f32(vals, cuda), n_docs)
+
+
+# ---------------------------------------------------------------------------------------------------- CSR build
+
+@pytest.mark.parametrize("case", ["A", "B"])
+def test_csr_build_matches_reference_golden(golden, cuda, case):
+    """add_batch_document + ndarray conversion of the REFERENCE (golden) vs the GPU radix-sort build: bit-exact."""
+    row, col, val = golden[f"{case}_row"], golden[f"{case}_col"], golden[f"{case}_val"]
+    if case == "B":   # feed order of the merged two-rank index: rank 0's postings, then rank 1's (merge_indexes)
+        order = np.concatenate([np.nonzero(row % 2 == r)[0] for r in range(2)])
+        row, col, val = row[order], col[order], val[order]
+    n_terms, n_docs = int(golden[f"{case}_n_terms"]), int(golden[f"{case}_n_docs"])
+    off, ids, w = ops.csr_build(dev_i32(row, cuda), dev_i32(col, cuda), dev_f32(val, cuda), n_terms, n_docs)
+    assert np.array_equal(off.cpu().numpy(), golden[f"{case}_offsets"])
+    assert np.array_equal(ids.cpu().numpy(), golden[f"{case}_ids"])
+    assert np.array_equal(w.cpu().numpy().view(np.uint32), golden[f"{case}_vals"].view(np.uint32))
+
+
+def test_csr_build_sort_docs_orders_unsorted_feed(golden, cuda):
+    row, col, val = golden["B_row"], golden["B_col"], golden["B_val"]
+    order = np.concatenate([np.nonzero(row % 2 == r)[0] for r in range(2)])
+    n_terms, n_docs = int(golden["B_n_terms"]), int(golden["B_n_docs"])
+    off, ids, w = ops.csr_build(dev_i32(row[order], cuda), dev_i32(col[order], cuda), dev_f32(val[order], cuda), n_terms, n_docs,
+                                sort_docs=True)
+    # row-major feed is already (doc asc) inside each term -> the doc-sorted build equals the oracle on the row-major feed
+    o_off, o_ids, o_w = sparse_oracle.build_csr(row, col, val, n_terms)
+    assert np.array_equal(off.cpu().numpy(), o_off)
+    assert np.array_equal(ids.cpu().numpy(), o_ids)
+    assert np.array_equal(w.cpu().numpy().view(np.uint32), o_w.view(np.uint32))
+
+
+@pytest.mark.parametrize("n_docs,n_terms,mean_nnz", [(1, 7, 3), (300, 5000, 40), (20000, 128256, 200), (70000, 1000, 30)])
+def test_csr_build_matches_oracle_random(cuda, n_docs, n_terms, mean_nnz):
+    rows, cols, vals = synth.gen_sparse_docs(n_docs, n_terms=n_terms, mean_nnz=mean_nnz, seed=7, device=cuda)
+    off, ids, w = ops.csr_build(rows, cols, vals, n_terms, n_docs)
+    o_off, o_ids, o_w = c_oracle.build_csr(rows.cpu().numpy(), cols.cpu().numpy(), vals.cpu().numpy(), n_terms)
+    assert np.array_equal(off.cpu().numpy(), o_off)
+    assert np.array_equal(ids.cpu().numpy(), o_ids)
+    assert np.array_equal(w.cpu().numpy().view(np.uint32), o_w.view(np.uint32))
+
+
+def test_csr_build_shuffled_feed_is_stable(cuda):
+    """Arbitrary feed order (not row-major): the build must keep feed order inside every term (stable)."""
+    rows, cols, vals = synth.gen_sparse_docs(5000, n_terms=300, mean_nnz=20, seed=11, device="cpu")
+    perm = torch.randperm(rows.numel(), generator=torch.Generator().manual_seed(3))
+    rows, cols, vals = rows[perm], cols[perm], vals[perm]
+    off, ids, w = ops.csr_build(rows.to(cuda), cols.to(cuda), vals.to(cuda), 300, 5000)
+    o_off, o_ids, o_w = c_oracle.build_csr(rows.numpy(), cols.numpy(), vals.numpy(), 300)
+    assert np.array_equal(off.cpu().numpy(), o_off)
+    assert np.array_equal(ids.cpu().numpy(), o_ids)
+    assert np.array_equal(w.cpu().numpy(), o_w)
+
+
+def test_csr_build_empty(cuda):
+    e = torch.empty(0, dtype=torch.int32, device=cuda)
+    off, ids, w = ops.csr_build(e, e.clone(), torch.empty(0, dtype=torch.float32, device=cuda), 17, 0)
+    assert off.cpu().tolist() == [0] * 18 and ids.numel() == 0 and w.numel() == 0
+
+
+def test_block_table_matches_searchsorted(golden, cuda):
+    off, ids = golden["C_offsets"], golden["C_ids"]
+    n_docs = int(golden["C_n_docs"])
+    index = build_index(off, ids, golden["C_vals"], n_docs, cuda)
+    bd = index.block_docs
+    n_blocks = (n_docs + bd - 1) // bd
+    table = index.table.cpu().numpy().view(np.uint32)
+    assert table.shape == (len(off) - 1, n_blocks + 1)
+    bounds = np.arange(n_blocks + 1) * bd
+    for t in range(len(off) - 1):
+        lst = ids[off[t]:off[t + 1]]
+        expect = off[t] + np.searchsorted(lst, bounds, side="left")
+        expect[-1] = off[t + 1]
+        assert np.array_equal(table[t], expect.astype(np.uint32)), t
+
+
+def test_block_table_rejects_unsorted_lists(golden, cuda):
+    from scaling_retriever_b200._lib import B200RetError
+    with pytest.raises(B200RetError) as err:
+        build_index(golden["B_offsets"], golden["B_ids"], golden["B_vals"], int(golden["B_n_docs"]), cuda)
+    assert err.value.code == -4
+
+
+# ---------------------------------------------------------------------------------------------------- scoring
+
+def golden_queries(golden):
+    return golden["C_q_offsets"], golden["C_q_terms"], golden["C_q_weights"]
+
+
+def test_scores_bit_exact_vs_reference_golden(golden, cuda):
+    """Full score vectors vs numba_score_float's (filtered, -scores) at threshold 0: identical rows, identical bits."""
+    n_docs = int(golden["C_n_docs"])
+    index = build_index(golden["C_offsets"], golden["C_ids"], golden["C_vals"], n_docs, cuda)
+    q_off, q_t, q_w = golden_queries(golden)
+    scores = ops.sparse_scores(index, dev_i32(q_off, cuda), dev_i32(q_t, cuda), dev_f32(q_w, cuda)).cpu().numpy()
+    assert scores.shape == (len(q_off) - 1, n_docs)
+    for ti, thr in enumerate(golden["C_thresholds"]):
+        for qi in range(len(q_off) - 1):
+            filtered = np.nonzero(scores[qi] > thr)[0]
+            assert np.array_equal(filtered, golden[f"C_t{ti}_q{qi}_filtered"])
+            assert np.array_equal((-scores[qi][filtered]).view(np.uint32), golden[f"C_t{ti}_q{qi}_neg_scores"].view(np.uint32))
+
+
+def check_topk_against_reference(ids_row, scores_row, count, ref_filtered, ref_neg_scores, k):
+    """The reference returns an unordered top-k set with arbitrary ties at the boundary (argpartition).  Rule: counts
+    equal; our scores (sorted desc) equal the reference's sorted scores bit-for-bit; every id we return has exactly
+    the reference score; ids strictly above the k-th score are identical sets."""
+    ref_scores = -ref_neg_scores
+    expect = min(k, len(ref_filtered))
+    assert count == expect
+    assert np.all(ids_row[count:] == -1) and np.all(np.isneginf(scores_row[count:]))
+    if count == 0:
+        return
+    ref_sorted = np.sort(ref_scores)[::-1][:count]
+    assert np.array_equal(scores_row[:count].view(np.uint32), ref_sorted.view(np.uint32))
+    lookup = dict(zip(ref_filtered.tolist(), ref_scores.tolist()))
+    for d, s in zip(ids_row[:count].tolist(), scores_row[:count].tolist()):
+        assert lookup[d] == s
+    kth = ref_sorted[-1]
+    above_ref = set(ref_filtered[ref_scores > kth].tolist())
+    above_ours = set(ids_row[:count][scores_row[:count] > kth].tolist())
+    assert above_ref == above_ours
+    # our deterministic tie rule: among docs tied at the k-th score the lowest row ids are kept, rows sorted (desc, id asc)
+    tied = np.sort(ref_filtered[ref_scores == kth])[:count - len(above_ref)]
+    assert set(tied.tolist()) == set(ids_row[:count][scores_row[:count] == kth].tolist())
+    order = np.lexsort((ids_row[:count], -scores_row[:count].astype(np.float64)))
+    assert np.array_equal(order, np.arange(count))
+
+
+@pytest.mark.parametrize("k", [10, 100, 1000])
+def test_search_matches_reference_golden(golden, cuda, k):
+    n_docs = int(golden["C_n_docs"])
+    index = build_index(golden["C_offsets"], golden["C_ids"], golden["C_vals"], n_docs, cuda)
+    q_off, q_t, q_w = golden_queries(golden)
+    for ti, thr in enumerate(golden["C_thresholds"]):
+        scores, ids, counts = ops.sparse_search(index, dev_i32(q_off, cuda), dev_i32(q_t, cuda), dev_f32(q_w, cuda), k, float(thr))
+        scores, ids, counts = scores.cpu().numpy(), ids.cpu().numpy(), counts.cpu().numpy()
+        for qi in range(len(q_off) - 1):
+            check_topk_against_reference(ids[qi], scores[qi], int(counts[qi]), golden[f"C_t{ti}_q{qi}_filtered"],
+                                         golden[f"C_t{ti}_q{qi}_neg_scores"], k)
+            # and against the reference's own select_topk output (as a sorted set of scores)
+            assert np.array_equal(np.sort(golden[f"C_t{ti}_q{qi}_k{k}_scores"])[::-1].view(np.uint32),
+                                  scores[qi][:counts[qi]].view(np.uint32))
+
+
+@pytest.mark.parametrize("n_docs,n_queries,k", [(100000, 1000, 1000), (30000, 64, 10), (3072 * 5 + 1, 33, 100)])
+def test_search_matches_oracle_synthetic(cuda, n_docs, n_queries, k):
+    """BASELINE config 1 shape (100k docs x Llama-3 vocab, 1k queries, top-1000) and ragged sizes vs the C oracle:
+    ids and scores identical (same total order on both sides)."""
+    rows, cols, vals = synth.gen_sparse_docs(n_docs, device=cuda)
+    index = ops.SparseDeviceIndex.from_coo(rows, cols, vals, synth.LLAMA3_VOCAB, n_docs)
+    q_off, q_t, q_w = synth.gen_sparse_queries(n_queries, device=cuda)
+    scores, ids, counts = ops.sparse_search(index, q_off, q_t, q_w, k, 0.0)
+    o_scores, o_ids, o_counts = c_oracle.sparse_search(index.term_offsets.cpu().numpy(), index.doc_ids.cpu().numpy(),
+                                                       index.weights.cpu().numpy(), n_docs, q_off.cpu().numpy(),
+                                                       q_t.cpu().numpy(), q_w.cpu().numpy(), k, 0.0)
+    assert np.array_equal(counts.cpu().numpy(), o_counts)
+    assert np.array_equal(ids.cpu().numpy(), o_ids)
+    assert np.array_equal(scores.cpu().numpy().view(np.uint32), o_scores.view(np.uint32))
+
+
+def test_search_long_query_and_negative_threshold(cuda):
+    """> 32 terms per query (two term groups in the kernel) and threshold < 0 (zero-score docs become eligible,
+    like np.zeros(N) > threshold in the reference)."""
+    n_docs, n_terms = 10000, 400
+    rows, cols, vals = synth.gen_sparse_docs(n_docs, n_terms=n_terms, mean_nnz=25, seed=5, device=cuda)
+    index = ops.SparseDeviceIndex.from_coo(rows, cols, vals, n_terms, n_docs)
+    q_off, q_t, q_w = synth.gen_sparse_queries(40, n_terms=n_terms, mean_nnz=70, seed=9, device=cuda)
+    assert int((q_off[1:] - q_off[:-1]).max()) > 32
+    for thr, k in [(0.0, 100), (-1.0, 4096), (2.5, 50)]:
+        scores, ids, counts = ops.sparse_search(index, q_off, q_t, q_w, k, thr)
+        o_scores, o_ids, o_counts = c_oracle.sparse_search(index.term_offsets.cpu().numpy(), index.doc_ids.cpu().numpy(),
+                                                           index.weights.cpu().numpy(), n_docs, q_off.cpu().numpy(),
+                                                           q_t.cpu().numpy(), q_w.cpu().numpy(), k, thr)
+        assert np.array_equal(counts.cpu().numpy(), o_counts)
+        assert np.array_equal(ids.cpu().numpy(), o_ids)
+        assert np.array_equal(scores.cpu().numpy().view(np.uint32), o_scores.view(np.uint32))
+
+
+def test_search_overflow_falls_back_to_safe_schedule(cuda):
+    """Adversarial doc order: scores increase with the row id, so every later doc beats the running k-th score and
+    the candidate lists overflow in the doubling rounds; the safe re-run must still return the exact top-k."""
+    n_docs, n_terms, k = 3072 * 40, 8, 10
+    rows = torch.arange(n_docs, dtype=torch.int32, device=cuda)
+    cols = torch.zeros(n_docs, dtype=torch.int32, device=cuda)
+    vals = (torch.arange(n_docs, dtype=torch.float32, device=cuda) + 1.0) / n_docs
+    index = ops.SparseDeviceIndex.from_coo(rows, cols, vals, n_terms, n_docs)
+    q_off = torch.tensor([0, 1, 1, 2], dtype=torch.int32, device=cuda)      # middle query is empty
+    q_t = torch.tensor([0, 0], dtype=torch.int32, device=cuda)
+    q_w = torch.tensor([1.0, 2.0], dtype=torch.float32, device=cuda)
+    scores, ids, counts = ops.sparse_search(index, q_off, q_t, q_w, k, 0.0)
+    assert counts.cpu().tolist() == [k, 0, k]
+    expect = np.arange(n_docs - 1, n_docs - 1 - k, -1)
+    assert np.array_equal(ids[0].cpu().numpy(), expect) and np.array_equal(ids[2].cpu().numpy(), expect)
+    assert np.array_equal(scores[2].cpu().numpy(), (2.0 * vals[expect.copy()].cpu().numpy()).astype(np.float32))
+
+
+def test_search_doc_id_base_and_empty_inputs(cuda):
+    n_docs, n_terms = 500, 50
+    rows, cols, vals = synth.gen_sparse_docs(n_docs, n_terms=n_terms, mean_nnz=5, seed=2, device=cuda)
+    index = ops.SparseDeviceIndex.from_coo(rows, cols, vals, n_terms, n_docs)
+    q_off, q_t, q_w = synth.gen_sparse_queries(5, n_terms=n_terms, mean_nnz=4, seed=3, device=cuda)
+    s0, i0, c0 = ops.sparse_search(index, q_off, q_t, q_w, 20, 0.0)
+    s1, i1, c1 = ops.sparse_search(index, q_off, q_t, q_w, 20, 0.0, doc_id_base=1000)
+    assert torch.equal(s0, s1) and torch.equal(c0, c1)
+    assert torch.equal(torch.where(i0 >= 0, i0 + 1000, i0), i1)
+    e_off = torch.zeros(1, dtype=torch.int32, device=cuda)
+    s, i, c = ops.sparse_search(index, e_off, q_t[:0], q_w[:0], 20, 0.0)
+    assert s.shape == (0, 20) and c.numel() == 0
+
+
+def test_ops_reject_cpu_tensors():
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.csr_build(torch.zeros(1, dtype=torch.int32), torch.zeros(1, dtype=torch.int32), torch.zeros(1), 4, 1)
