@@ -44,6 +44,14 @@ const char* b200ret_last_error(void);
 /* Device facts the host side needs for grid sizing / sanity (cudaGetDeviceProperties). */
 int b200ret_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin_bytes);
 
+/* Measurement hooks (bench.py): when enabled, the dominant kernels are bracketed with CUDA events on the
+ * launching stream.  kind: 0 sparse score kernel, 1 sparse select kernels, 2 dense GEMM+top-k kernel,
+ * 3 CSR radix-sort passes.  b200ret_profile_read synchronises the device, returns the summed duration
+ * (ms) and count of the timed launches of `kind` since the last read, plus the number of ALL kernels
+ * this library launched since the last read with all_launches != NULL (then reset). */
+int b200ret_profile_enable(int on);
+int b200ret_profile_read(int kind, double* total_ms, int64_t* timed_launches, int64_t* all_launches);
+
 /* ------------------------------------------------------------------------------------------------
  * (1) Sparse index build: COO -> CSR posting lists.
  * Replaces IndexDictOfArray.add_batch_document (scaling_retriever/utils/inverted_index.py:67-76) and

@@ -22,6 +22,8 @@ PROTOTYPES = {
     "b200ret_last_error": (ctypes.c_char_p, []),
     "b200ret_device_info": (_c_int, [ctypes.POINTER(_c_int), ctypes.POINTER(_c_int), ctypes.POINTER(_c_int),
                                      ctypes.POINTER(_c_sz)]),
+    "b200ret_profile_enable": (_c_int, [_c_int]),
+    "b200ret_profile_read": (_c_int, [_c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_c_i64), ctypes.POINTER(_c_i64)]),
     "b200ret_csr_build_workspace_bytes": (_c_sz, [_c_i64, _c_i32, _c_i32, _c_int]),
     "b200ret_csr_build": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i32, _c_i32, _c_int,
                                    _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_sz, _c_ptr]),

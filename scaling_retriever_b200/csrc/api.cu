@@ -1,6 +1,8 @@
 // Library-level pieces of the C ABI: version, error text, device facts.
 #include <stdarg.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace b200ret {
@@ -30,7 +32,73 @@ int sm_count() {
     return cached;
 }
 
+// ---- launch accounting + per-kernel CUDA-event timing (bench.py's roofline leg) -------------------------------
+namespace {
+struct ProfileState {
+    bool enabled = false;
+    long long launches = 0;
+    std::vector<cudaEvent_t> pool;                 // recycled events
+    std::vector<cudaEvent_t> begin[PROF_KINDS], end[PROF_KINDS];
+};
+ProfileState g_prof;
+cudaEvent_t take_event() {
+    if (!g_prof.pool.empty()) {
+        cudaEvent_t e = g_prof.pool.back();
+        g_prof.pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+}  // namespace
+
+void count_launches(int n) { g_prof.launches += n; }
+
+void prof_begin(int kind, cudaStream_t stream) {
+    if (!g_prof.enabled) return;
+    cudaEvent_t e = take_event();
+    cudaEventRecord(e, stream);
+    g_prof.begin[kind].push_back(e);
+}
+
+void prof_end(int kind, cudaStream_t stream) {
+    if (!g_prof.enabled) return;
+    cudaEvent_t e = take_event();
+    cudaEventRecord(e, stream);
+    g_prof.end[kind].push_back(e);
+}
+
 }  // namespace b200ret
+
+extern "C" int b200ret_profile_enable(int on) {
+    b200ret::g_prof.enabled = on != 0;
+    return B200RET_OK;
+}
+
+extern "C" int b200ret_profile_read(int kind, double* total_ms, int64_t* timed_launches, int64_t* all_launches) {
+    using namespace b200ret;
+    B200RET_REQUIRE(kind >= 0 && kind < PROF_KINDS, "profile_read: bad kind %d", kind);
+    B200RET_CUDA_CHECK(cudaDeviceSynchronize());
+    double ms = 0.0;
+    const size_t n = g_prof.end[kind].size();
+    for (size_t i = 0; i < n; ++i) {
+        float t = 0.f;
+        B200RET_CUDA_CHECK(cudaEventElapsedTime(&t, g_prof.begin[kind][i], g_prof.end[kind][i]));
+        ms += t;
+        g_prof.pool.push_back(g_prof.begin[kind][i]);
+        g_prof.pool.push_back(g_prof.end[kind][i]);
+    }
+    g_prof.begin[kind].clear();
+    g_prof.end[kind].clear();
+    if (total_ms) *total_ms = ms;
+    if (timed_launches) *timed_launches = static_cast<int64_t>(n);
+    if (all_launches) {
+        *all_launches = g_prof.launches;
+        g_prof.launches = 0;
+    }
+    return B200RET_OK;
+}
 
 extern "C" int b200ret_version(void) { return B200RET_VERSION; }
 

@@ -51,6 +51,13 @@ struct Workspace {
 
 int sm_count();
 
+// Launch accounting / optional per-kernel CUDA-event timing on the launching stream (see b200ret_profile_*).
+constexpr int PROF_KINDS = 4;
+constexpr int PROF_SPARSE_SCORE = 0, PROF_SPARSE_SELECT = 1, PROF_DENSE_GEMM = 2, PROF_CSR_SORT = 3;
+void count_launches(int n);
+void prof_begin(int kind, cudaStream_t stream);
+void prof_end(int kind, cudaStream_t stream);
+
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;

@@ -318,9 +318,12 @@ extern "C" int b200ret_csr_build(const int32_t* rows, const int32_t* cols, const
         p.dst_val = last ? weights : (to_a ? a_val : b_val);
         p.key_is_row = plan.key_is_row[i]; p.shift = plan.shift[i]; p.bits = plan.bits[i];
         const int buckets = 1 << p.bits;
+        prof_begin(PROF_CSR_SORT, stream);
         sort_hist_kernel<<<grid, SORT_THREADS, 0, stream>>>(p, nnz, per_block, counts);
         sort_scan_kernel<<<1, 1024, 0, stream>>>(counts, buckets * grid);
         sort_scatter_kernel<<<grid, SORT_THREADS, 0, stream>>>(p, nnz, per_block, counts);
+        prof_end(PROF_CSR_SORT, stream);
+        count_launches(3);
         B200RET_CUDA_CHECK(cudaGetLastError());
         src_row = p.dst_row; src_col = p.dst_col; src_val = p.dst_val;
         sorted_col = p.dst_col;

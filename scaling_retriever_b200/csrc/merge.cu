@@ -92,6 +92,7 @@ extern "C" int b200ret_merge_topk(const float* in_scores, const int64_t* in_ids,
     }
     merge_topk_kernel<<<n_queries, MERGE_THREADS, smem, stream>>>(in_scores, in_ids, n_shards, n_queries, k, out_scores,
                                                                   out_ids, out_counts);
+    count_launches(1);
     B200RET_CUDA_CHECK(cudaGetLastError());
     return B200RET_OK;
 }

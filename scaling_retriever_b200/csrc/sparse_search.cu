@@ -311,16 +311,26 @@ int run_rounds(ScoreParams sp, const SearchBuffers& b, int32_t n_queries, int32_
         sp.blk_begin = blk;
         sp.blk_end = end;
         B200RET_CUDA_CHECK(cudaMemsetAsync(b.item_counter, 0, sizeof(unsigned long long), stream));
+        prof_begin(PROF_SPARSE_SCORE, stream);
         sparse_score_kernel<<<grid, SCORE_THREADS, score_smem, stream>>>(sp);
-        if (end < n_blocks)
+        prof_end(PROF_SPARSE_SCORE, stream);
+        count_launches(1);
+        if (end < n_blocks) {
+            prof_begin(PROF_SPARSE_SELECT, stream);
             select_kernel<false><<<sp.n_active, SELECT_THREADS, select_smem, stream>>>(
                 b.cand, b.cand_count, sp.cap, k, b.tau, b.overflow, n_queries, sp.q_list, doc_id_base, nullptr, nullptr, nullptr);
+            prof_end(PROF_SPARSE_SELECT, stream);
+            count_launches(1);
+        }
         B200RET_CUDA_CHECK(cudaGetLastError());
         blk = end;
         if (!safe) size = blk;   // doubling: the next round covers as many docs as all rounds so far
     }
+    prof_begin(PROF_SPARSE_SELECT, stream);
     select_kernel<true><<<sp.n_active, SELECT_THREADS, select_smem, stream>>>(
         b.cand, b.cand_count, sp.cap, k, b.tau, b.overflow, n_queries, sp.q_list, doc_id_base, out_scores, out_ids, out_counts);
+    prof_end(PROF_SPARSE_SELECT, stream);
+    count_launches(1);
     B200RET_CUDA_CHECK(cudaGetLastError());
     return B200RET_OK;
 }
@@ -413,6 +423,7 @@ extern "C" int b200ret_sparse_search(const uint32_t* table, const int32_t* doc_i
 
     const int init_grid = (n_queries + 255) / 256;
     search_init_kernel<<<init_grid, 256, 0, stream>>>(b.tau, b.cand_count, b.overflow, n_queries, threshold);
+    count_launches(1);
     B200RET_CUDA_CHECK(cudaGetLastError());
     int rc = run_rounds(sp, b, n_queries, k, n_blocks, /*safe=*/false, doc_id_base, out_scores, out_ids, out_counts, stream);
     if (rc != B200RET_OK) return rc;

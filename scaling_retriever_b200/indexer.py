@@ -370,6 +370,7 @@ class SparseRetrieval:
             self.l0 = L0()
         self.model.to(self._cuda)
         self._ext_ids = None
+        self._staging = {}
 
     def _generate_query_vecs(self, q_loader):
         sparse_query_vecs = []
@@ -397,14 +398,57 @@ class SparseRetrieval:
         Copies through pinned memory; this is the call bench.py times end to end."""
         dev = self._cuda
         with torch.cuda.device(dev):
-            d_off = torch.from_numpy(np.ascontiguousarray(q_offsets, dtype=np.int32)).pin_memory().to(dev, non_blocking=True)
-            d_terms = torch.from_numpy(np.ascontiguousarray(q_terms, dtype=np.int32)).pin_memory().to(dev, non_blocking=True)
-            d_w = torch.from_numpy(np.ascontiguousarray(q_weights, dtype=np.float32)).pin_memory().to(dev, non_blocking=True)
+            d_off = self._stage_in("q_off", q_offsets, torch.int32)
+            d_terms = self._stage_in("q_terms", q_terms, torch.int32)
+            d_w = self._stage_in("q_w", q_weights, torch.float32)
             scores, ids, counts = ops.sparse_search(self.device_index, d_off, d_terms, d_w, int(topk), float(threshold),
                                                     doc_id_base=self.doc_id_base)
             if self.shard_plan.world_size > 1:
                 scores, ids, counts = shard.merge_shards(scores, ids, int(topk))
-            return scores.cpu().numpy(), ids.cpu().numpy(), counts.cpu().numpy()
+            out = [self._stage_out(name, t) for name, t in (("scores", scores), ("ids", ids), ("counts", counts))]
+            torch.cuda.current_stream().synchronize()
+            return tuple(o.numpy() for o in out)
+
+    def _pinned(self, name, shape, dtype):
+        """Reusable pinned host staging buffers (grown on demand) so host<->device copies run at full PCIe rate."""
+        need = int(np.prod(shape)) if len(shape) else 1
+        buf = self._staging.get(name)
+        if buf is None or buf.dtype != dtype or buf.numel() < need:
+            buf = torch.empty(max(need, 1), dtype=dtype, pin_memory=True)
+            self._staging[name] = buf
+        return buf[:need].view(shape)
+
+    def _stage_in(self, name, host_array, dtype):
+        src = torch.from_numpy(np.ascontiguousarray(host_array)).to(dtype)
+        pinned = self._pinned(name, tuple(src.shape), dtype)
+        pinned.copy_(src)
+        return pinned.to(self._cuda, non_blocking=True)
+
+    def _stage_out(self, name, dev_tensor):
+        pinned = self._pinned(name, tuple(dev_tensor.shape), dev_tensor.dtype)
+        pinned.copy_(dev_tensor, non_blocking=True)
+        return pinned
+
+    @classmethod
+    def from_device_index(cls, device_index, doc_ids=None, doc_id_base=0, size_collection=None, out_dir=None):
+        """Wrap an index that is already resident in HBM (bench.py, tests): no encoder, no files."""
+        self = cls.__new__(cls)
+        self.model = None
+        self._cuda = device_index.device
+        self.device = self._cuda.index
+        self.sparse_index = None
+        self.device_index = device_index
+        self.doc_id_base = doc_id_base
+        self.size_collection = device_index.n_docs if size_collection is None else size_collection
+        self.shard_plan = shard.ShardPlan(self.size_collection, _world_size())
+        self.doc_ids = doc_ids if doc_ids is not None else range(self.size_collection)
+        self.dim_voc = device_index.n_terms
+        self.out_dir = out_dir
+        self.compute_stats = False
+        self.doc_stats = None
+        self._ext_ids = None
+        self._staging = {}
+        return self
 
     def score_float(self, indexes_to_retrieve, query_values, threshold):
         """API analogue of the reference's numba_score_float (indexer.py:324-344) for ONE query, on the GPU:
@@ -425,7 +469,7 @@ class SparseRetrieval:
                 for k, v in self.doc_ids.items():
                     ext[k] = v
             else:
-                ext[:len(self.doc_ids)] = self.doc_ids
+                ext[:len(self.doc_ids)] = list(self.doc_ids)
             self._ext_ids = ext
         return self._ext_ids
 

@@ -42,6 +42,22 @@ def device_info():
     return {"sm_count": sm.value, "cc": (major.value, minor.value), "smem_optin_bytes": smem.value}
 
 
+PROF_SPARSE_SCORE, PROF_SPARSE_SELECT, PROF_DENSE_GEMM, PROF_CSR_SORT = 0, 1, 2, 3
+
+
+def profile_enable(on=True):
+    """Bracket the dominant kernels with CUDA events on the launching stream (bench.py's roofline leg)."""
+    _lib.check(_lib.load().b200ret_profile_enable(int(bool(on))))
+
+
+def profile_read(kind):
+    """(summed ms, timed launches of `kind`, all kernel launches of the library) since the last read; syncs the device."""
+    import ctypes
+    ms, n, total = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64()
+    _lib.check(_lib.load().b200ret_profile_read(int(kind), ctypes.byref(ms), ctypes.byref(n), ctypes.byref(total)))
+    return ms.value, n.value, total.value
+
+
 def csr_build(rows, cols, vals, n_terms, n_docs, sort_docs=False):
     """COO postings in feed order -> (term_offsets int64[V+1], doc_ids int32[nnz], weights fp32[nnz]).
 

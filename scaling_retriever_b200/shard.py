@@ -49,11 +49,13 @@ def gather_candidates(scores, ids, group=None):
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return scores.unsqueeze(0).contiguous(), ids.unsqueeze(0).contiguous()
-    all_scores = torch.empty((world,) + tuple(scores.shape), dtype=scores.dtype, device=scores.device)
-    all_ids = torch.empty((world,) + tuple(ids.shape), dtype=ids.dtype, device=ids.device)
+    q, k = scores.shape
+    # concatenated-along-dim-0 output form: accepted by both NCCL and gloo
+    all_scores = torch.empty((world * q, k), dtype=scores.dtype, device=scores.device)
+    all_ids = torch.empty((world * q, k), dtype=ids.dtype, device=ids.device)
     dist.all_gather_into_tensor(all_scores, scores.contiguous(), group=group)
     dist.all_gather_into_tensor(all_ids, ids.contiguous(), group=group)
-    return all_scores, all_ids
+    return all_scores.view(world, q, k), all_ids.view(world, q, k)
 
 
 def merge_shards(scores, ids, k, group=None):

@@ -1,0 +1,68 @@
+"""world_size-2 test of the shard-merge plumbing on CPU (gloo): each rank searches its doc-range shard with the
+oracle (standing in for the GPU kernel, which cannot run here), the candidates are all-gathered with
+shard.gather_candidates, and the merged result must equal the unsharded search.  The merge itself is checked against
+the same total order the merge_topk kernel implements (its GPU parity test is tests/test_merge_gpu.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def merge_rows_reference(all_scores, all_ids, k):
+    """numpy restatement of merge_topk's contract: [G, Q, k] -> [Q, k] under (score desc, id asc), -1 ids dropped."""
+    g, q, _ = all_scores.shape
+    out_s = np.full((q, k), -np.inf, dtype=np.float32)
+    out_i = np.full((q, k), -1, dtype=np.int64)
+    counts = np.zeros(q, dtype=np.int32)
+    for qi in range(q):
+        s = all_scores[:, qi, :].reshape(-1)
+        i = all_ids[:, qi, :].reshape(-1)
+        live = i >= 0
+        s, i = s[live], i[live]
+        order = np.lexsort((i, -s.astype(np.float64)))[:k]
+        out_s[qi, :len(order)], out_i[qi, :len(order)], counts[qi] = s[order], i[order], len(order)
+    return out_s, out_i, counts
+
+
+def _worker(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import c_oracle
+    from scaling_retriever_b200 import shard, synth
+    n_docs, n_terms, k = 5000, 300, 25
+    rows, cols, vals = synth.gen_sparse_docs(n_docs, n_terms=n_terms, mean_nnz=12, seed=21)
+    off, ids, w = c_oracle.build_csr(rows.numpy(), cols.numpy(), vals.numpy(), n_terms)
+    q_off, q_t, q_w = (x.numpy() for x in synth.gen_sparse_queries(17, n_terms=n_terms, mean_nnz=6, seed=22))
+    lo, hi = shard.ShardPlan(n_docs, world).bounds(rank)
+    s_off, s_ids, s_w = shard.shard_sparse_csr(torch.as_tensor(off), torch.as_tensor(ids), torch.as_tensor(w), lo, hi)
+    scores, lids, _ = c_oracle.sparse_search(s_off.numpy(), s_ids.numpy(), s_w.numpy(), hi - lo, q_off, q_t, q_w, k)
+    gids = np.where(lids >= 0, lids + lo, -1)
+    all_scores, all_ids = shard.gather_candidates(torch.as_tensor(scores), torch.as_tensor(gids))
+    assert all_scores.shape == (world, 17, k)
+    merged = merge_rows_reference(all_scores.numpy(), all_ids.numpy(), k)
+    full = c_oracle.sparse_search(off, ids, w, n_docs, q_off, q_t, q_w, k)
+    ok = all(np.array_equal(a, b) for a, b in zip(merged, full))
+    np.save(os.path.join(tmp, f"ok_{rank}.npy"), np.array([ok]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_shard_gather_merge_equals_unsharded(tmp_path):
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert bool(np.load(tmp_path / f"ok_{r}.npy")[0])
+
+
+def test_merge_reference_total_order():
+    s = np.array([[[3., 1., -np.inf]], [[3., 2., 2.]]], dtype=np.float32)
+    i = np.array([[[5, 9, -1]], [[4, 7, 6]]], dtype=np.int64)
+    out_s, out_i, c = merge_rows_reference(s, i, 4)
+    assert out_i.tolist() == [[4, 5, 6, 7]] and out_s.tolist() == [[3., 3., 2., 2.]] and c.tolist() == [4]
