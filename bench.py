@@ -144,7 +144,7 @@ def run_b200(args):
     del rows, cols, vals
     torch.cuda.empty_cache()
     t0 = time.perf_counter()
-    index = ops.SparseDeviceIndex.from_csr(term_offsets, doc_ids, weights, hi - lo)
+    index = ops.SparseDeviceIndex.from_csr(term_offsets, doc_ids, weights, hi - lo, copy=False)   # slices bank-ordered in place
     torch.cuda.synchronize()
     table_s = time.perf_counter() - t0
 

@@ -86,6 +86,15 @@ int b200ret_block_table_build(const int64_t* term_offsets, const int32_t* doc_id
                               int32_t n_terms, int32_t n_docs, int32_t block_docs,
                               uint32_t* table, int32_t* status, void* stream);
 
+/* Search-side layout optimisation, in place, after b200ret_block_table_build: inside every (term, doc
+ * block) slice the postings are rewritten in bank-quantile order (bank = doc id mod 32; every bank's
+ * postings are spread evenly over the slice), so that 32 consecutive postings hold about the even share
+ * 32*c/len of each bank instead of runs, which halves the bank conflicts of the score tile.  The multiset
+ * of postings per slice is unchanged (scores are unaffected: a doc occurs once per list); lists are no
+ * longer ascending afterwards, so the table must not be rebuilt from the reordered arrays. */
+int b200ret_sparse_bank_order(const uint32_t* table, int32_t* doc_ids, float* weights, int32_t n_terms,
+                              int32_t n_docs, int32_t block_docs, void* stream);
+
 /* Doc-block size (documents per warp-private accumulator tile) compiled into the search kernel. */
 int32_t b200ret_sparse_block_docs(void);
 

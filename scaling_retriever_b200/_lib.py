@@ -28,6 +28,7 @@ PROTOTYPES = {
     "b200ret_csr_build": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i32, _c_i32, _c_int,
                                    _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_sz, _c_ptr]),
     "b200ret_block_table_build": (_c_int, [_c_ptr, _c_ptr, _c_i64, _c_i32, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_ptr]),
+    "b200ret_sparse_bank_order": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_ptr]),
     "b200ret_sparse_block_docs": (_c_i32, []),
     "b200ret_sparse_search_workspace_bytes": (_c_sz, [_c_i32, _c_i32]),
     "b200ret_sparse_search": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32,
@@ -64,7 +65,7 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
-        path = _build.LIB_PATH
+        path = os.environ.get("B200RET_LIB") or _build.LIB_PATH   # override: tuning builds of the same sources
         if not os.path.exists(path):
             try:
                 _build.build()

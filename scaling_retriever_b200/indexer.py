@@ -351,16 +351,10 @@ class SparseRetrieval:
         # The index moves to HBM once, for the lifetime of the retriever (replaces the numba.typed.Dict copy, :365-370).
         with torch.cuda.device(self._cuda):
             self.sparse_index.device = self._cuda
-            full = self.sparse_index.device_index()
             self.shard_plan = shard.ShardPlan(self.size_collection, _world_size())
-            if self.shard_plan.world_size > 1:
-                lo, hi = self.shard_plan.bounds(_rank())
-                off, ids, w = shard.shard_sparse_csr(full.term_offsets, full.doc_ids, full.weights, lo, hi)
-                self.device_index = ops.SparseDeviceIndex.from_csr(off, ids, w, hi - lo)
-                self.doc_id_base = lo
-            else:
-                self.device_index = full
-                self.doc_id_base = 0
+            lo, hi = self.shard_plan.bounds(_rank()) if self.shard_plan.world_size > 1 else (0, self.size_collection)
+            self.device_index = self.sparse_index.device_index(lo, hi)
+            self.doc_id_base = lo
 
         self.out_dir = os.path.join(config["out_dir"], dataset_name) if (dataset_name is not None and not is_beir) \
             else config["out_dir"]

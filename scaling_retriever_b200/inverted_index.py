@@ -229,10 +229,16 @@ class IndexDictOfArray:
         json.dump(index_dist, open(os.path.join(self.index_path, "index_dist.json"), "w"))
 
     # ---- search-side view -----------------------------------------------------------------------------------
-    def device_index(self):
-        """Doc-sorted CSR + doc-block skip table on the GPU (what SparseRetrieval searches)."""
+    def device_index(self, doc_lo=0, doc_hi=None):
+        """Search-side index on the GPU for doc rows [doc_lo, doc_hi) (default: all; row ids become local to the range):
+        doc-sorted CSR + doc-block skip table, slices in bank order.  The canonical CSR of this object is not modified."""
         off, ids, w = self.finalize()
         n_docs = int(self.n)
+        if doc_lo != 0 or (doc_hi is not None and doc_hi != n_docs):
+            from . import shard
+            doc_hi = n_docs if doc_hi is None else doc_hi
+            off, ids, w = shard.shard_sparse_csr(off, ids, w, doc_lo, doc_hi)
+            n_docs = doc_hi - doc_lo
         try:
             return ops.SparseDeviceIndex.from_csr(off, ids, w, n_docs)
         except Exception as exc:   # lists not ascending (merged multi-rank index): re-sort by (term, doc) on the GPU

@@ -120,15 +120,24 @@ class SparseDeviceIndex:
         return self.doc_ids.device
 
     @classmethod
-    def from_csr(cls, term_offsets, doc_ids, weights, n_docs):
+    def from_csr(cls, term_offsets, doc_ids, weights, n_docs, bank_order=True, copy=True):
+        """Wrap a doc-sorted CSR.  `bank_order` rewrites every (term, doc block) slice in shared-memory-bank order for
+        the search kernel; with `copy` (default) that happens on clones so the caller's canonical CSR stays intact."""
         table = block_table_build(term_offsets, doc_ids, n_docs)
-        return cls(term_offsets, doc_ids, weights, table, term_offsets.numel() - 1, int(n_docs), block_docs())
+        n_terms = term_offsets.numel() - 1
+        if bank_order and doc_ids.numel():
+            if copy:
+                doc_ids, weights = doc_ids.clone(), weights.clone()
+            with torch.cuda.device(doc_ids.device):
+                _lib.check(_lib.load().b200ret_sparse_bank_order(_ptr(table), _ptr(doc_ids), _ptr(weights), n_terms, int(n_docs),
+                                                                 block_docs(), _stream()))
+        return cls(term_offsets, doc_ids, weights, table, n_terms, int(n_docs), block_docs())
 
     @classmethod
     def from_coo(cls, rows, cols, vals, n_terms, n_docs):
         """Build from COO postings in any order (lists come out ascending in doc id)."""
         term_offsets, doc_ids, weights = csr_build(rows, cols, vals, n_terms, n_docs, sort_docs=True)
-        return cls.from_csr(term_offsets, doc_ids, weights, n_docs)
+        return cls.from_csr(term_offsets, doc_ids, weights, n_docs, copy=False)
 
 
 def sparse_search(index, q_offsets, q_terms, q_weights, k, threshold=0.0, doc_id_base=0):

@@ -105,6 +105,34 @@ def test_block_table_rejects_unsorted_lists(golden, cuda):
     assert err.value.code == -4
 
 
+def test_bank_order_permutes_inside_slices_only(golden, cuda):
+    """b200ret_sparse_bank_order: every (term, doc block) slice keeps its multiset of (doc, weight) postings, and a window
+    of 32 consecutive postings holds at most one more than the even share ceil(32*c/len) of any shared-memory bank
+    (doc % 32, c = postings of that bank in the slice)."""
+    rows, cols, vals = synth.gen_sparse_docs(40000, n_terms=300, mean_nnz=40, seed=13, device=cuda)
+    off, ids, w = ops.csr_build(rows, cols, vals, 300, 40000)
+    index = ops.SparseDeviceIndex.from_csr(off, ids, w, 40000)            # bank-ordered copy
+    assert index.doc_ids.data_ptr() != ids.data_ptr()
+    table = index.table.cpu().numpy().view(np.uint32)
+    a_ids, a_w = ids.cpu().numpy(), w.cpu().numpy()
+    b_ids, b_w = index.doc_ids.cpu().numpy(), index.weights.cpu().numpy()
+    worst = 0
+    for t in range(0, 300, 7):
+        for b in range(table.shape[1] - 1):
+            lo, hi = int(table[t, b]), int(table[t, b + 1])
+            if hi - lo == 0:
+                continue
+            oa, ob = np.argsort(a_ids[lo:hi]), np.argsort(b_ids[lo:hi])
+            assert np.array_equal(a_ids[lo:hi][oa], b_ids[lo:hi][ob]) and np.array_equal(a_w[lo:hi][oa], b_w[lo:hi][ob])
+            share = np.ceil(32.0 * np.bincount(b_ids[lo:hi] & 31, minlength=32) / (hi - lo))
+            for s0 in range(0, hi - lo, 32):
+                got = np.bincount(b_ids[lo + s0:min(hi, lo + s0 + 32)] & 31, minlength=32)
+                worst = max(worst, int((got - share).max()))
+    assert worst <= 1
+    keep = ops.SparseDeviceIndex.from_csr(off, ids, w, 40000, bank_order=False)
+    assert keep.doc_ids.data_ptr() == ids.data_ptr()
+
+
 # ---------------------------------------------------------------------------------------------------- scoring
 
 def golden_queries(golden):
