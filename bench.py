@@ -164,6 +164,10 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # nvidia-smi is started BEFORE the warm-up: attaching to the driver stalls the GPU for tens of ms, which must not land
+    # in the timed region; the samples it takes during warm-up + timed steps are all under the same load.
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.5)
     for _ in range(args.warmup):
         step()
     ops.profile_read(ops.PROF_SPARSE_SCORE)     # drop warm-up records and launch counts
@@ -171,7 +175,6 @@ def run_b200(args):
 
     # ---- device-resident throughput (`value`) ----------------------------------------------------------------
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     for _ in range(args.steps):
@@ -272,6 +275,164 @@ def cpu_baseline(term_offsets, doc_ids, weights, n_docs, h_off, h_terms, h_w, gp
                       f"oracle/sparse_oracle.c with {threads} OpenMP threads", "gpu_rows_identical": match}
 
 
+def dense_workload_name(n_docs, n_queries, dim):
+    cfg = "configs[2]" if dim == 2048 else ("configs[3]" if dim == 4096 else "configs[4] sweep point")
+    return (f"dense flat inner-product top-{K_TOP}, synthetic {n_docs:,} x {dim} bf16 corpus (L2-normalised Gaussian rows), "
+            f"{n_queries:,} queries [BASELINE.json {cfg}]")
+
+
+def run_b200_dense(args):
+    """Dense workload (BASELINE.json configs[2]/[3]): bf16 tcgen05 GEMM + fused top-k over a doc-range shard per GPU."""
+    import torch.distributed as dist
+    from scaling_retriever_b200 import ops, shard
+    from scaling_retriever_b200.indexer import DenseFlatIndexer
+
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch N>1 with torchrun)"
+    peaks = load_peaks()
+    n_docs = args.n_docs or synth.MSMARCO_DOCS
+    n_queries = args.n_queries or synth.MSMARCO_DEV_QUERIES
+    dim = args.dim
+    lo, hi = shard.ShardPlan(n_docs, world).bounds(rank)
+    corpus = synth.gen_dense(n_docs, dim, seed=1234, device=dev, dtype=torch.bfloat16, row_lo=lo, row_hi=hi)
+    q32 = synth.gen_dense(n_queries, dim, seed=4321, device=dev)
+    q16 = ops.f32_to_bf16(q32)
+    h_q = q32.cpu().numpy()
+    flops = 2.0 * n_queries * (hi - lo) * dim
+
+    def step():
+        s, i, c = ops.dense_search(corpus, q16, K_TOP, doc_id_base=lo)
+        if world > 1:
+            s, i, c = shard.merge_shards(s, i, K_TOP)
+        return s, i, c
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ops.profile_enable(True)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.5)
+    for _ in range(args.warmup):
+        step()
+    ops.profile_read(ops.PROF_DENSE_GEMM)
+    ops.profile_read(ops.PROF_SPARSE_SELECT)
+    barrier()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(args.steps):
+        out = step()
+    end.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_total = torch.tensor([start.elapsed_time(end)], device=dev)
+    gemm_ms, gemm_launches, all_launches = ops.profile_read(ops.PROF_DENSE_GEMM)
+    select_ms, _, _ = ops.profile_read(ops.PROF_SPARSE_SELECT)
+    ops.profile_enable(False)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms_total.item()) / args.steps
+    value = n_queries / (ms_per_step / 1e3)
+
+    # end to end through the class API: host fp32 queries -> pinned -> device cast -> search (-> merge) -> host rows
+    index = DenseFlatIndexer(device=dev)
+    index.init_index(dim)
+    index.index = corpus
+    index._row_lo = lo
+    for _ in range(2):
+        index.search_arrays(h_q, K_TOP)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e_scores, e_ids = index.search_arrays(h_q, K_TOP)
+    barrier()
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / args.steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    assert np.array_equal(e_ids, out[1].cpu().numpy())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    achieved = flops * args.steps / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": dense_workload_name(n_docs, n_queries, dim), "n_docs": n_docs, "n_queries": n_queries, "k": K_TOP,
+                   "dim": dim, "parallelism": f"doc-range shards x{world} + NCCL all-gather merge" if world > 1 else "1 GPU",
+                   "l2": "inputs larger than L2 (corpus shard %.1f GB vs 126 MB L2), no flush" % ((hi - lo) * dim * 2 / 1e9)},
+        "e2e": {"value": n_queries / float(e2e_s.item()), "unit": UNIT, "h2d_bytes_per_step": int(h_q.nbytes),
+                "d2h_bytes_per_step": int(e_scores.nbytes + e_ids.nbytes)},
+        "gpu_launches": int(all_launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "dense_search_kernel", "achieved": achieved, "peak": peaks["bf16_tflops"],
+                     "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+                     "frac_of_sustained_peak": achieved / peaks["bf16_tflops_sustained"], "launches": int(gemm_launches),
+                     "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "algorithmic_flops_per_step": flops,
+                     "gemm_kernel_share_of_step": (gemm_ms / args.steps) / ms_per_step,
+                     "select_kernels_ms_per_step": select_ms / args.steps},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = dense_cpu_baseline(corpus, h_q, out, n_docs)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def dense_cpu_baseline(corpus, h_q, gpu_out, n_docs, sample_docs=200_000, sample_queries=512):
+    """fp32 restatement of faiss.IndexFlatIP.search (oracle/dense_oracle.py, torch/MKL sgemm + top-k; faiss-cpu itself is not
+    installable here) on a bounded slice of the same corpus; QPS is scaled linearly in N to the full corpus."""
+    from oracle import dense_oracle
+    nd, nq = min(sample_docs, corpus.shape[0]), min(sample_queries, len(h_q))
+    docs = corpus[:nd].float().cpu().numpy()
+    qs = torch.from_numpy(h_q[:nq]).to(torch.bfloat16).float().numpy()
+    t0 = time.perf_counter()
+    o_scores, o_ids = dense_oracle.flat_ip_search(docs, qs, K_TOP)
+    dt = time.perf_counter() - t0
+    return {"value": nq / (dt * n_docs / nd), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{nq} queries x first {nd} docs in {dt:.1f} s (fp32 restatement of IndexFlatIP, not faiss), scaled "
+                      f"linearly in N to {n_docs} docs"}
+
+
+def run_reference_dense(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    from oracle import dense_oracle
+    n_docs = args.n_docs or synth.MSMARCO_DOCS
+    n_queries = args.n_queries or synth.MSMARCO_DEV_QUERIES
+    nd, nq = min(200_000, n_docs), min(512, n_queries)
+    docs = synth.gen_dense(n_docs, args.dim, seed=1234, row_lo=0, row_hi=nd).numpy()
+    qs = synth.gen_dense(n_queries, args.dim, seed=4321, row_lo=0, row_hi=nq).numpy()
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        dense_oracle.flat_ip_search(docs, qs, K_TOP)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    s_per_step = sum(times) / len(times)
+    value = nq / (s_per_step * n_docs / nd)
+    sample = (f"{nq} queries x first {nd} docs per step (fp32 restatement of faiss IndexFlatIP: torch/MKL sgemm + top-k), QPS "
+              f"scaled linearly in N to {n_docs} docs")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": dense_workload_name(n_docs, n_queries, args.dim), "n_docs": n_docs, "n_queries": n_queries,
+                   "k": K_TOP, "dim": args.dim},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
 def run_reference(args):
     """Reference arm: the CPU port of the reference's sparse retrieval path, all host threads, bounded sample per step."""
     rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
@@ -317,12 +478,15 @@ def main():
     ap.add_argument("--n-docs", type=int, default=0, help="override the corpus size (debug; the headline is 8,841,823)")
     ap.add_argument("--n-queries", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="sparse", choices=["sparse", "dense"],
+                    help="sparse = BASELINE.json configs[1] (default, the headline); dense = configs[2]/[3]")
+    ap.add_argument("--dim", type=int, default=2048, help="dense row width (2048 = Lion-DS-1B, 4096 = Lion-DS-8B)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
-        run_reference(args)
+        (run_reference_dense if args.workload == "dense" else run_reference)(args)
     else:
-        run_b200(args)
+        (run_b200_dense if args.workload == "dense" else run_b200)(args)
 
 
 if __name__ == "__main__":

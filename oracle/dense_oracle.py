@@ -33,14 +33,15 @@ def flat_ip_search(corpus, queries, k, block=65536):
             best_s = torch.gather(best_s, 1, order)
             best_i = torch.gather(best_i, 1, order)
             # re-sort kept block by id within equal scores is preserved by stability on the next round
-    if best_s.shape[1] < k:
-        pad = k - best_s.shape[1]
-        best_s = torch.cat([best_s, torch.full((q, pad), -float("inf"))], dim=1)
-        best_i = torch.cat([best_i, torch.full((q, pad), -1, dtype=torch.int64)], dim=1)
-    else:
+    if best_s.shape[1]:
+        # kept rows are (score desc, id asc) and a new block's ids are larger, so one stable sort restores the total order
         order = torch.sort(best_s, dim=1, descending=True, stable=True).indices[:, :k]
         best_s = torch.gather(best_s, 1, order)
         best_i = torch.gather(best_i, 1, order)
+    if best_s.shape[1] < k:   # fewer than k rows in the index: faiss pads with label -1
+        pad = k - best_s.shape[1]
+        best_s = torch.cat([best_s, torch.full((q, pad), -float("inf"))], dim=1)
+        best_i = torch.cat([best_i, torch.full((q, pad), -1, dtype=torch.int64)], dim=1)
     return best_s.numpy(), best_i.numpy()
 
 

@@ -118,3 +118,6 @@ def test_dense_oracle_is_exact_topk():
         np.testing.assert_allclose(scores[i], full[i][order], rtol=1e-6)
     scores, labels = dense_oracle.flat_ip_search(docs[:5], qs, 8)
     assert np.all(labels[:, 5:] == -1) and np.all(np.isneginf(scores[:, 5:]))
+    assert np.all(np.diff(scores[:, :5], axis=1) <= 0)
+    for i in range(7):
+        assert np.array_equal(labels[i, :5], np.argsort(-(qs[i] @ docs[:5].T), kind="stable"))
