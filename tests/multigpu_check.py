@@ -1,0 +1,79 @@
+"""Multi-GPU parity check, run under torchrun (one rank per GPU, NCCL):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/multigpu_check.py
+
+Every rank searches its doc-range shard (sparse and dense), the per-shard top-k rows are all-gathered over NCCL and merged by
+the merge_topk kernel; the result on EVERY rank must be identical (ids and score bits) to the unsharded search of the whole
+corpus on one GPU.  Driven by tests/test_multigpu.py when >= 2 GPUs are visible.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from scaling_retriever_b200 import ops, shard, synth  # noqa: E402
+from scaling_retriever_b200.indexer import DenseFlatIndexer, SparseRetrieval  # noqa: E402
+from scaling_retriever_b200.inverted_index import IndexDictOfArray  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+
+    # ---- sparse: ops level -------------------------------------------------------------------------------------------
+    n_docs, n_terms, n_queries, k = 60011, 3000, 150, 100
+    rows, cols, vals = synth.gen_sparse_docs(n_docs, n_terms=n_terms, mean_nnz=50, seed=5, device=dev)
+    q_off, q_t, q_w = synth.gen_sparse_queries(n_queries, n_terms=n_terms, mean_nnz=12, seed=6, device=dev)
+    full = ops.SparseDeviceIndex.from_coo(rows, cols, vals, n_terms, n_docs)
+    ref_s, ref_i, ref_c = ops.sparse_search(full, q_off, q_t, q_w, k, 0.0)
+    lo, hi = shard.ShardPlan(n_docs, world).bounds(rank)
+    keep = (rows >= lo) & (rows < hi)
+    part = ops.SparseDeviceIndex.from_coo((rows[keep] - lo).contiguous(), cols[keep].contiguous(), vals[keep].contiguous(),
+                                          n_terms, hi - lo)
+    s, i, c = ops.sparse_search(part, q_off, q_t, q_w, k, 0.0, doc_id_base=lo)
+    s, i, c = shard.merge_shards(s, i, k)
+    assert torch.equal(i, ref_i) and torch.equal(c, ref_c) and torch.equal(s.view(torch.int32), ref_s.view(torch.int32)), "sparse ops"
+
+    # ---- sparse: class API (SparseRetrieval shards by itself under a process group) ------------------------------------
+    index = IndexDictOfArray(index_path=None, dim_voc=n_terms, device=dev)
+    index.add_batch_document(rows, cols, vals, n_docs=n_docs)
+    retr = SparseRetrieval(torch.nn.Linear(1, 1), {"out_dir": "/tmp"}, n_terms, local,
+                           index_d={"index": index, "ids_mapping": {d: f"D{d}" for d in range(n_docs)}})
+    assert retr.doc_id_base == lo and retr.device_index.n_docs == hi - lo
+    h = retr.search_arrays(q_off.cpu().numpy(), q_t.cpu().numpy(), q_w.cpu().numpy(), k, 0.0)
+    assert np.array_equal(h[1], ref_i.cpu().numpy()) and np.array_equal(h[0].view(np.uint32), ref_s.cpu().numpy().view(np.uint32))
+    res, _ = retr._sparse_retrieve_multithreaded(synth.queries_to_vecs(q_off, q_t, q_w), list(range(n_queries)), 0.0, k)
+    assert res["3"][f"D{int(ref_i[3, 0])}"] == float(ref_s[3, 0])
+
+    # ---- dense ---------------------------------------------------------------------------------------------------------
+    nd, dim, nq, kd = 30007, 256, 70, 200
+    docs = synth.gen_dense(nd, dim, seed=7, device=dev, dtype=torch.bfloat16)
+    queries = synth.gen_dense(nq, dim, seed=8, device=dev)
+    q16 = ops.f32_to_bf16(queries)
+    ref_s, ref_i, _ = ops.dense_search(docs, q16, kd)
+    lo, hi = shard.ShardPlan(nd, world).bounds(rank)
+    s, i, _ = ops.dense_search(docs[lo:hi].contiguous(), q16, kd, doc_id_base=lo)
+    s, i, _ = shard.merge_shards(s, i, kd)
+    assert torch.equal(i, ref_i) and torch.equal(s.view(torch.int32), ref_s.view(torch.int32)), "dense ops"
+    flat = DenseFlatIndexer(device=dev)
+    flat.init_index(dim)
+    flat.index_data(docs.float().cpu().numpy(), [f"P{j}" for j in range(nd)])
+    assert flat.index.shape[0] == hi - lo
+    top_ids, top_scores = flat.search_knn(queries.cpu().numpy(), kd)
+    assert top_ids[5][0] == f"P{int(ref_i[5, 0])}" and np.array_equal(top_scores, ref_s.cpu().numpy())
+
+    dist.barrier()
+    if rank == 0:
+        print(f"multigpu_check ok: world_size={world}, sharded sparse + dense results identical to the single-GPU search")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
