@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(uint64_t* cand, 
                                                                        float* out_scores, int64_t* out_ids, int32_t* out_counts) {
     extern __shared__ __align__(16) uint64_t skeys[];
     __shared__ uint32_t hist[256];
-    __shared__ uint64_t bcast[2];
+    __shared__ uint64_t bcast[3];
     __shared__ int out_pos;
     const int q = q_list ? q_list[blockIdx.x] : blockIdx.x;
     uint64_t* cq = cand + static_cast<size_t>(q) * cap;

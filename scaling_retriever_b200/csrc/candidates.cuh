@@ -15,6 +15,7 @@
 namespace b200ret {
 
 constexpr int SELECT_THREADS = 512;
+constexpr int ROUND_GROWTH = 4;   // total docs scored grow 4x per round (4, 16, 64, ... units)
 
 struct CandBuffers {
     uint64_t* cand;        // [n_queries][cap] keys (cand_key)
@@ -66,7 +67,9 @@ int run_rounds_once(LaunchRound& launch_round, const CandBuffers& b, int32_t cap
             if (rc != B200RET_OK) return rc;
         }
         unit = end;
-        if (!safe) size = unit;   // doubling: the next round covers as many docs as all rounds so far
+        // geometric schedule: the next round covers (ROUND_GROWTH - 1) x the docs seen so far, so about
+        // (ROUND_GROWTH - 1) * k new candidates per query survive tau on exchangeable data (capacity is >= k + 8 k)
+        if (!safe) size = unit * (ROUND_GROWTH - 1);
     }
     return launch_select(true, b, cap, k, n_queries, n_active, q_list, doc_id_base, out_scores, out_ids, out_counts, stream);
 }

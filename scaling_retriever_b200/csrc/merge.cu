@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_topk_kernel(const float* 
                                                                    int64_t* out_ids, int32_t* out_counts) {
     extern __shared__ __align__(16) uint64_t skeys[];
     __shared__ uint32_t hist[256];
-    __shared__ uint64_t bcast[2];
+    __shared__ uint64_t bcast[3];
     __shared__ int n_live;
     const int q = blockIdx.x;
     if (threadIdx.x == 0) n_live = 0;

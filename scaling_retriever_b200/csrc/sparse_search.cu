@@ -28,12 +28,18 @@
 namespace b200ret {
 
 constexpr int ROUND0_BLOCKS = 4;       // first round / safe-schedule round size, in doc blocks
+#ifndef B200RET_LDNC            // posting-load flavour (tuning knob)
+#define B200RET_LDNC "ld.global.nc"
+#endif
+#ifndef B200RET_LOOKAHEAD       // prefetch the next term group's skip-table entries (tuning knob)
+#define B200RET_LOOKAHEAD 1
+#endif
 #ifndef B200RET_STEP_ROWS
 #define B200RET_STEP_ROWS 4
 #endif
 constexpr int STEP_ROWS = B200RET_STEP_ROWS;     // rows (of 32 postings) fetched per pipeline step (2 or 4)
 #ifndef B200RET_PIPE_DEPTH
-#define B200RET_PIPE_DEPTH 6
+#define B200RET_PIPE_DEPTH 5     // 6 spills a few registers at 128 regs/thread and measures slower
 #endif
 constexpr int PIPE_DEPTH = B200RET_PIPE_DEPTH;   // steps in flight per warp (register ring)
 
@@ -101,17 +107,36 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const Sc
         const uint32_t acc_rel_s = static_cast<uint32_t>(__cvta_generic_to_shared(acc)) - static_cast<uint32_t>(doc_base) * 4u;
         const int qb = p.q_offsets[q], qe = p.q_offsets[q + 1];
 
-        for (int g = qb; g < qe; g += 32) {
-            // Lane j holds term g+j of the query: its weight and its posting slice inside this doc block.
-            unsigned seg_beg = 0, seg_end = 0;
-            float seg_qw = 0.f;
+        // Lane j holds term g+j of the query: its weight and its posting slice inside this doc block.  The lookup of
+        // the NEXT group of 32 terms (query term -> skip table, two dependent loads) is issued before the current
+        // group is streamed, so its latency is paid once per item, not once per group.
+        auto lookup = [&](int g, unsigned& beg, unsigned& end, float& qw) {
+            beg = 0;
+            end = 0;
+            qw = 0.f;
             if (g + static_cast<int>(lane) < qe) {
                 const int t = __ldg(p.q_terms + g + lane);
-                seg_qw = __ldg(p.q_weights + g + lane);
+                qw = __ldg(p.q_weights + g + lane);
                 const uint32_t* e = g_table + static_cast<size_t>(t) * table_stride + blk;
-                seg_beg = __ldg(e);
-                seg_end = __ldg(e + 1);
+                beg = __ldg(e);
+                end = __ldg(e + 1);
             }
+        };
+#if B200RET_LOOKAHEAD
+        unsigned nxt_beg, nxt_end;
+        float nxt_qw;
+        lookup(qb, nxt_beg, nxt_end, nxt_qw);
+#endif
+        for (int g = qb; g < qe; g += 32) {
+#if B200RET_LOOKAHEAD
+            const unsigned seg_beg = nxt_beg, seg_end = nxt_end;
+            const float seg_qw = nxt_qw;
+            if (g + 32 < qe) lookup(g + 32, nxt_beg, nxt_end, nxt_qw);
+#else
+            unsigned seg_beg, seg_end;
+            float seg_qw;
+            lookup(g, seg_beg, seg_end, seg_qw);
+#endif
             unsigned pending = __ballot_sync(FULL, seg_end > seg_beg);   // non-empty slices, ascending term order
             // Publish the descriptors: the cursor reads slice j with three broadcast LDS.32 (3 wavefronts) instead of
             // three SHFLs (4 wavefronts each on the same, saturated, L1 data pipe).
@@ -126,7 +151,10 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const Sc
             // Fetch one step into registers (ids = -1 on dead lanes).  Returns false when nothing is left.
             // Everything is predicated per lane: uniform branches around the rows past a short slice were measured
             // slower (register ring spills, lost overlap) than the dead L1 data-pipe slots they save.
-            auto fetch = [&](int (&id)[R], float (&w)[R], float& qw) -> bool {
+            // A step's liveness is (rel + 32*row < len) per lane: rel = position of the lane in row 0 relative to the
+            // slice begin (wraps to a huge value before the slice), len = slice length (0 = empty step).  The loads leave
+            // dead lanes' registers unwritten (no initialisation moves); consume() re-derives the same predicates.
+            auto fetch = [&](int (&id)[R], float (&w)[R], float& qw, unsigned& rel, unsigned& len) -> bool {
                 bool more = true;
                 if (c_row >= c_end) {                      // warp-uniform: current slice exhausted
                     if (pending != 0) {
@@ -141,19 +169,32 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const Sc
                     }
                 }
                 qw = c_qw;
-                const int32_t* __restrict__ ids_row = g_ids + c_row;     // one 64-bit address per array and step;
-                const float* __restrict__ w_row = g_w + c_row;           // rows use immediate offsets
-                const unsigned rel = c_row + lane - c_beg;                // wraps (huge) for positions before the slice
-                const unsigned len = more ? c_end - c_beg : 0u;
-#pragma unroll
-                for (int k = 0; k < R; ++k) {
-                    id[k] = -1;
-                    w[k] = 0.f;
-                    if (rel + 32u * k < len) {
-                        id[k] = __ldg(ids_row + 32 * k);
-                        w[k] = __ldg(w_row + 32 * k);
-                    }
-                }
+                rel = c_row + lane - c_beg;
+                len = more ? c_end - c_beg : 0u;
+                const int32_t* ids_row = g_ids + c_row;     // one 64-bit address per array and step; rows use immediates
+                const float* w_row = g_w + c_row;
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred p0, p1, p2, p3;\n\t"
+                    ".reg .u32 t1, t2, t3;\n\t"
+                    "add.u32 t1, %8, 32;\n\t"
+                    "add.u32 t2, %8, 64;\n\t"
+                    "add.u32 t3, %8, 96;\n\t"
+                    "setp.lt.u32 p0, %8, %9;\n\t"
+                    "setp.lt.u32 p1, t1, %9;\n\t"
+                    "setp.lt.u32 p2, t2, %9;\n\t"
+                    "setp.lt.u32 p3, t3, %9;\n\t"
+                    "@p0 " B200RET_LDNC ".u32 %0, [%10];\n\t"
+                    "@p0 " B200RET_LDNC ".f32 %4, [%11];\n\t"
+                    "@p1 " B200RET_LDNC ".u32 %1, [%10 + 128];\n\t"
+                    "@p1 " B200RET_LDNC ".f32 %5, [%11 + 128];\n\t"
+                    "@p2 " B200RET_LDNC ".u32 %2, [%10 + 256];\n\t"
+                    "@p2 " B200RET_LDNC ".f32 %6, [%11 + 256];\n\t"
+                    "@p3 " B200RET_LDNC ".u32 %3, [%10 + 384];\n\t"
+                    "@p3 " B200RET_LDNC ".f32 %7, [%11 + 384];\n\t"
+                    "}\n"
+                    : "=r"(id[0]), "=r"(id[1]), "=r"(id[2]), "=r"(id[3]), "=f"(w[0]), "=f"(w[1]), "=f"(w[2]), "=f"(w[3])
+                    : "r"(rel), "r"(len), "l"(ids_row), "l"(w_row));
                 c_row += 32u * R;
                 return more;
             };
@@ -161,57 +202,43 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const Sc
             // read-modify-writes are independent: loads, adds and stores are issued R-wide (one latency per step).
             // reference arithmetic: scores[doc] += q * w  -> fp32 multiply, then fp32 add (no FMA); dead lanes
             // (id < 0) are predicated off.
-            auto consume = [&](const int (&id)[R], const float (&w)[R], float qw) {
-                static_assert(R == 4 || R == 2, "the accumulate blocks are written for 2 or 4 rows per step");
-                const float v0 = __fmul_rn(qw, w[0]), v1 = __fmul_rn(qw, w[1]);
-                if constexpr (R == 4) {
-                    const float v2 = __fmul_rn(qw, w[2]), v3 = __fmul_rn(qw, w[3]);
-                    asm volatile(
-                        "{\n\t"
-                        ".reg .pred p0, p1, p2, p3;\n\t"
-                        ".reg .f32 a0, a1, a2, a3;\n\t"
-                        ".reg .u32 d0, d1, d2, d3;\n\t"
-                        "setp.ge.s32 p0, %0, 0;\n\t"
-                        "setp.ge.s32 p1, %1, 0;\n\t"
-                        "setp.ge.s32 p2, %2, 0;\n\t"
-                        "setp.ge.s32 p3, %3, 0;\n\t"
-                        "mad.lo.u32 d0, %0, 4, %8;\n\t"
-                        "mad.lo.u32 d1, %1, 4, %8;\n\t"
-                        "mad.lo.u32 d2, %2, 4, %8;\n\t"
-                        "mad.lo.u32 d3, %3, 4, %8;\n\t"
-                        "@p0 ld.shared.f32 a0, [d0];\n\t"
-                        "@p1 ld.shared.f32 a1, [d1];\n\t"
-                        "@p2 ld.shared.f32 a2, [d2];\n\t"
-                        "@p3 ld.shared.f32 a3, [d3];\n\t"
-                        "@p0 add.rn.f32 a0, a0, %4;\n\t"
-                        "@p1 add.rn.f32 a1, a1, %5;\n\t"
-                        "@p2 add.rn.f32 a2, a2, %6;\n\t"
-                        "@p3 add.rn.f32 a3, a3, %7;\n\t"
-                        "@p0 st.shared.f32 [d0], a0;\n\t"
-                        "@p1 st.shared.f32 [d1], a1;\n\t"
-                        "@p2 st.shared.f32 [d2], a2;\n\t"
-                        "@p3 st.shared.f32 [d3], a3;\n\t"
-                        "}\n" ::"r"(id[0]), "r"(id[1]), "r"(id[R - 2]), "r"(id[R - 1]), "f"(v0), "f"(v1), "f"(v2), "f"(v3), "r"(acc_rel_s)
-                        : "memory");
-                } else {
-                    asm volatile(
-                        "{\n\t"
-                        ".reg .pred p0, p1;\n\t"
-                        ".reg .f32 a0, a1;\n\t"
-                        ".reg .u32 d0, d1;\n\t"
-                        "setp.ge.s32 p0, %0, 0;\n\t"
-                        "setp.ge.s32 p1, %1, 0;\n\t"
-                        "mad.lo.u32 d0, %0, 4, %4;\n\t"
-                        "mad.lo.u32 d1, %1, 4, %4;\n\t"
-                        "@p0 ld.shared.f32 a0, [d0];\n\t"
-                        "@p1 ld.shared.f32 a1, [d1];\n\t"
-                        "@p0 add.rn.f32 a0, a0, %2;\n\t"
-                        "@p1 add.rn.f32 a1, a1, %3;\n\t"
-                        "@p0 st.shared.f32 [d0], a0;\n\t"
-                        "@p1 st.shared.f32 [d1], a1;\n\t"
-                        "}\n" ::"r"(id[0]), "r"(id[1]), "f"(v0), "f"(v1), "r"(acc_rel_s)
-                        : "memory");
-                }
+            auto consume = [&](const int (&id)[R], const float (&w)[R], float qw, unsigned rel, unsigned len) {
+                static_assert(R == 4, "the fetch/accumulate blocks are written for 4 rows per step");
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred p0, p1, p2, p3;\n\t"
+                    ".reg .f32 a0, a1, a2, a3, v0, v1, v2, v3;\n\t"
+                    ".reg .u32 d0, d1, d2, d3, t1, t2, t3;\n\t"
+                    "add.u32 t1, %9, 32;\n\t"
+                    "add.u32 t2, %9, 64;\n\t"
+                    "add.u32 t3, %9, 96;\n\t"
+                    "setp.lt.u32 p0, %9, %10;\n\t"
+                    "setp.lt.u32 p1, t1, %10;\n\t"
+                    "setp.lt.u32 p2, t2, %10;\n\t"
+                    "setp.lt.u32 p3, t3, %10;\n\t"
+                    "mad.lo.u32 d0, %0, 4, %11;\n\t"
+                    "mad.lo.u32 d1, %1, 4, %11;\n\t"
+                    "mad.lo.u32 d2, %2, 4, %11;\n\t"
+                    "mad.lo.u32 d3, %3, 4, %11;\n\t"
+                    "@p0 ld.shared.f32 a0, [d0];\n\t"
+                    "@p1 ld.shared.f32 a1, [d1];\n\t"
+                    "@p2 ld.shared.f32 a2, [d2];\n\t"
+                    "@p3 ld.shared.f32 a3, [d3];\n\t"
+                    "mul.rn.f32 v0, %8, %4;\n\t"
+                    "mul.rn.f32 v1, %8, %5;\n\t"
+                    "mul.rn.f32 v2, %8, %6;\n\t"
+                    "mul.rn.f32 v3, %8, %7;\n\t"
+                    "@p0 add.rn.f32 a0, a0, v0;\n\t"
+                    "@p1 add.rn.f32 a1, a1, v1;\n\t"
+                    "@p2 add.rn.f32 a2, a2, v2;\n\t"
+                    "@p3 add.rn.f32 a3, a3, v3;\n\t"
+                    "@p0 st.shared.f32 [d0], a0;\n\t"
+                    "@p1 st.shared.f32 [d1], a1;\n\t"
+                    "@p2 st.shared.f32 [d2], a2;\n\t"
+                    "@p3 st.shared.f32 [d3], a3;\n\t"
+                    "}\n" ::"r"(id[0]), "r"(id[1]), "r"(id[2]), "r"(id[3]), "f"(w[0]), "f"(w[1]), "f"(w[2]), "f"(w[3]), "f"(qw),
+                    "r"(rel), "r"(len), "r"(acc_rel_s)
+                    : "memory");
                 __syncwarp();   // orders this step's shared-memory updates before the next step (possibly the next term)
             };
 
@@ -220,20 +247,21 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const Sc
             constexpr int S = PIPE_DEPTH;
             int id[S][R];
             float w[S][R], qw[S];
+            unsigned rel[S], len[S];
             bool more[S];
 #pragma unroll
-            for (int s = 0; s < S - 1; ++s) more[s] = fetch(id[s], w[s], qw[s]);
+            for (int s = 0; s < S - 1; ++s) more[s] = fetch(id[s], w[s], qw[s], rel[s], len[s]);
             bool running = true;
             while (running) {
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                     const int f = (s + S - 1) % S;                 // slot freed by the previous consume
-                    more[f] = fetch(id[f], w[f], qw[f]);
+                    more[f] = fetch(id[f], w[f], qw[f], rel[f], len[f]);
                     if (!more[s]) {                                // oldest step is empty: nothing is left at all
                         running = false;
                         break;
                     }
-                    consume(id[s], w[s], qw[s]);
+                    consume(id[s], w[s], qw[s], rel[s], len[s]);
                 }
             }
             __syncwarp();   // the descriptors are rewritten by the next term group

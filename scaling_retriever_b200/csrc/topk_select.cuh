@@ -13,12 +13,31 @@
 namespace b200ret {
 
 // MSB-first 8-bit radix select: returns the k-th largest key (1 <= k <= n) of keys[0..n).
-// `hist` is 256 shared counters, `bcast` two shared u64 slots.  All threads of the block call it.
+// `hist` is 256 shared counters, `bcast` three shared u64 slots.  All threads of the block call it.
+// Early exit: as soon as the bucket that holds the k-th key contains exactly as many keys as are still needed, every key
+// of that bucket is selected and the k-th key is simply the bucket's minimum (one min pass instead of the remaining digit
+// passes; with fp32 scores in the high half this happens after 3-4 of the 8 passes).
 __device__ inline uint64_t block_radix_select_kth(const uint64_t* keys, int n, int k, uint32_t* hist,
                                                   uint64_t* bcast) {
     uint64_t prefix = 0, mask = 0;
     int remaining = k;
     for (int shift = 56; shift >= 0; shift -= 8) {
+        if (shift < 56 && static_cast<int>(bcast[2]) == remaining) {   // bucket size == keys still needed (block-uniform)
+            if (threadIdx.x == 0) bcast[0] = ~0ull;
+            __syncthreads();
+            unsigned long long lo = ~0ull;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const uint64_t key = keys[i];
+                if ((key & mask) == prefix) lo = min(lo, static_cast<unsigned long long>(key));
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+            if ((threadIdx.x & 31) == 0 && lo != ~0ull) atomicMin(reinterpret_cast<unsigned long long*>(bcast), lo);
+            __syncthreads();
+            const uint64_t kth = bcast[0];
+            __syncthreads();
+            return kth;
+        }
         for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
         __syncthreads();
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -48,6 +67,7 @@ __device__ inline uint64_t block_radix_select_kth(const uint64_t* keys, int n, i
                     if (above + c[j] >= static_cast<uint32_t>(remaining)) {
                         bcast[0] = static_cast<uint64_t>(255 - (threadIdx.x * 8 + j));
                         bcast[1] = static_cast<uint64_t>(remaining - above);
+                        bcast[2] = static_cast<uint64_t>(c[j]);      // size of the chosen bucket
                         break;
                     }
                     above += c[j];

@@ -55,6 +55,29 @@ def _cuda_device(device):
     return torch.device("cuda", torch.cuda.current_device())
 
 
+def _pinned(staging, name, shape, dtype):
+    """Reusable pinned host staging buffers (grown on demand) so host<->device copies run at full PCIe rate."""
+    need = int(np.prod(shape)) if len(shape) else 1
+    buf = staging.get(name)
+    if buf is None or buf.dtype != dtype or buf.numel() < need:
+        buf = torch.empty(max(need, 1), dtype=dtype, pin_memory=True)
+        staging[name] = buf
+    return buf[:need].view(shape)
+
+
+def _stage_in(staging, device, name, host_array, dtype):
+    src = torch.from_numpy(np.ascontiguousarray(host_array)).to(dtype)
+    pinned = _pinned(staging, name, tuple(src.shape), dtype)
+    pinned.copy_(src)
+    return pinned.to(device, non_blocking=True)
+
+
+def _stage_out(staging, name, dev_tensor):
+    pinned = _pinned(staging, name, tuple(dev_tensor.shape), dev_tensor.dtype)
+    pinned.copy_(dev_tensor, non_blocking=True)
+    return pinned
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # dense: embeddings dump (unchanged format) + flat inner-product index
 # ------------------------------------------------------------------------------------------------------------------
@@ -181,6 +204,7 @@ class DenseFlatIndexer(DenseIndexer):
         self.device = device
         self.hidden_dim = None
         self._row_lo = 0
+        self._staging = {}
 
     def init_index(self, hidden_dim):
         self.device = _cuda_device(self.device)
@@ -208,19 +232,22 @@ class DenseFlatIndexer(DenseIndexer):
 
     def search_arrays(self, query_reps, top_docs):
         """(scores fp32 [Q, k] descending, row labels int64 [Q, k], -1 padded) as host numpy arrays."""
-        q = torch.from_numpy(np.ascontiguousarray(query_reps, dtype=np.float32)).to(self.device)
-        q16 = ops.f32_to_bf16(q)
-        scores, ids, _ = ops.dense_search(self.index, q16, int(top_docs), doc_id_base=self._row_lo)
-        if _world_size() > 1:
-            scores, ids, _ = shard.merge_shards(scores, ids, int(top_docs))
-        return scores.cpu().numpy(), ids.cpu().numpy()
+        with torch.cuda.device(self.device):
+            q = _stage_in(self._staging, self.device, "queries", query_reps, torch.float32)   # pinned -> device
+            q16 = ops.f32_to_bf16(q)
+            scores, ids, _ = ops.dense_search(self.index, q16, int(top_docs), doc_id_base=self._row_lo)
+            if _world_size() > 1:
+                scores, ids, _ = shard.merge_shards(scores, ids, int(top_docs))
+            out_s, out_i = _stage_out(self._staging, "scores", scores), _stage_out(self._staging, "ids", ids)
+            torch.cuda.current_stream().synchronize()
+            return out_s.numpy(), out_i.numpy()
 
     def search_knn(self, query_reps: np.array, top_docs: int):
         scores, indexes = self.search_arrays(query_reps, top_docs)
         # reference indexer.py:212 (a -1 label indexes the last id there; kept identical)
         id_arr = self.index_id_to_db_id
         top_doc_ids = [[id_arr[idx] for idx in per_query_indexes] for per_query_indexes in indexes.tolist()]
-        return top_doc_ids, scores
+        return top_doc_ids, scores.copy()   # search_arrays returns views of reusable pinned staging buffers
 
     def get_index_name(self):
         return "flat_index"
@@ -403,25 +430,11 @@ class SparseRetrieval:
             torch.cuda.current_stream().synchronize()
             return tuple(o.numpy() for o in out)
 
-    def _pinned(self, name, shape, dtype):
-        """Reusable pinned host staging buffers (grown on demand) so host<->device copies run at full PCIe rate."""
-        need = int(np.prod(shape)) if len(shape) else 1
-        buf = self._staging.get(name)
-        if buf is None or buf.dtype != dtype or buf.numel() < need:
-            buf = torch.empty(max(need, 1), dtype=dtype, pin_memory=True)
-            self._staging[name] = buf
-        return buf[:need].view(shape)
-
     def _stage_in(self, name, host_array, dtype):
-        src = torch.from_numpy(np.ascontiguousarray(host_array)).to(dtype)
-        pinned = self._pinned(name, tuple(src.shape), dtype)
-        pinned.copy_(src)
-        return pinned.to(self._cuda, non_blocking=True)
+        return _stage_in(self._staging, self._cuda, name, host_array, dtype)
 
     def _stage_out(self, name, dev_tensor):
-        pinned = self._pinned(name, tuple(dev_tensor.shape), dev_tensor.dtype)
-        pinned.copy_(dev_tensor, non_blocking=True)
-        return pinned
+        return _stage_out(self._staging, name, dev_tensor)
 
     @classmethod
     def from_device_index(cls, device_index, doc_ids=None, doc_id_base=0, size_collection=None, out_dir=None):
