@@ -227,19 +227,25 @@ __global__ void block_table_empty_kernel(const int64_t* __restrict__ term_offset
 // is rewritten in bank-quantile order (every bank's postings spread evenly over the slice): a window of 32 consecutive
 // postings then holds about its even share 32*c/len of each bank instead of runs.  One warp per slice, slice staged in
 // shared memory, in place.
-constexpr int BANK_WARPS = 4;
+// Implementation: posting i of bank b with in-bank rank r (of c) gets the integer key floor((2r+1) * len / (2c)) in
+// [0, len) - its quantile position in the slice; keys of one bank are >= len/c >= 1 apart, so a key value holds at most one
+// posting per bank.  A counting sort over the key values (shared-memory histogram + warp scan) then yields the permutation:
+// one integer division per posting instead of a comparison sort.
+constexpr int BANK_WARPS = 3;
 constexpr int BANK_MAX_BLOCK_DOCS = 4096;
+constexpr int BANK_WARP_SMEM = BANK_MAX_BLOCK_DOCS * 16 + 128;   // ids, weights, (key, slot), key counters + 32 bank counters
 
 __global__ void __launch_bounds__(BANK_WARPS * 32) bank_order_kernel(const uint32_t* __restrict__ table, int32_t* __restrict__ doc_ids,
                                                                       float* __restrict__ weights, int32_t n_terms, int32_t n_blocks) {
     extern __shared__ __align__(16) unsigned char bank_smem[];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
-    unsigned char* mine = bank_smem + static_cast<size_t>(warp) * (BANK_MAX_BLOCK_DOCS * 10 + 128);
+    unsigned char* mine = bank_smem + static_cast<size_t>(warp) * BANK_WARP_SMEM;
     int32_t* s_ids = reinterpret_cast<int32_t*>(mine);
     float* s_w = reinterpret_cast<float*>(mine + BANK_MAX_BLOCK_DOCS * 4);
-    uint16_t* s_rank = reinterpret_cast<uint16_t*>(mine + BANK_MAX_BLOCK_DOCS * 8);
-    uint32_t* hist = reinterpret_cast<uint32_t*>(mine + BANK_MAX_BLOCK_DOCS * 10);
+    uint32_t* s_key = reinterpret_cast<uint32_t*>(mine + BANK_MAX_BLOCK_DOCS * 8);     // pass 1: in-bank rank; pass 2: key << 8 | slot
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(mine + BANK_MAX_BLOCK_DOCS * 12);    // postings per key value -> exclusive offsets
+    uint32_t* hist = reinterpret_cast<uint32_t*>(mine + BANK_MAX_BLOCK_DOCS * 16);
     const size_t row_len = static_cast<size_t>(n_blocks) + 1;
     const int groups = (n_blocks + 31) / 32;
     const long long n_items = static_cast<long long>(n_terms) * groups;
@@ -259,31 +265,39 @@ __global__ void __launch_bounds__(BANK_WARPS * 32) bank_order_kernel(const uint3
             const uint32_t s_beg = __shfl_sync(0xffffffffu, beg, j);
             const int len = static_cast<int>(__shfl_sync(0xffffffffu, end, j) - s_beg);
             hist[lane] = 0;
+            for (int i = lane; i < len; i += 32) s_cnt[i] = 0;
             __syncwarp();
-            for (int i = lane; i < len; i += 32) {
+            for (int i = lane; i < len; i += 32) {             // stage the slice, rank every posting inside its bank
                 const int32_t d = doc_ids[s_beg + i];
                 s_ids[i] = d;
                 s_w[i] = weights[s_beg + i];
-                s_rank[i] = static_cast<uint16_t>(atomicAdd(&hist[d & 31], 1u));
+                s_key[i] = atomicAdd(&hist[d & 31], 1u);
+            }
+            __syncwarp();
+            for (int i = lane; i < len; i += 32) {             // quantile key + slot inside the key's bin (<= 1 per bank)
+                const uint32_t r = s_key[i];
+                const uint32_t c = hist[s_ids[i] & 31];
+                const uint32_t key = ((2u * r + 1u) * static_cast<uint32_t>(len)) / (2u * c);   // < len; products < 2^26
+                const uint32_t slot = atomicAdd(&s_cnt[key], 1u);
+                s_key[i] = (key << 8) | slot;
+            }
+            __syncwarp();
+            uint32_t carry = 0;                                 // exclusive scan of the bin sizes, 32 bins per step
+            for (int base = 0; base < len; base += 32) {
+                const uint32_t v = (base + lane < len) ? s_cnt[base + lane] : 0u;
+                uint32_t incl = v;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xffffffffu, incl, off);
+                    if (lane >= off) incl += u;
+                }
+                if (base + lane < len) s_cnt[base + lane] = carry + incl - v;
+                carry += __shfl_sync(0xffffffffu, incl, 31);
             }
             __syncwarp();
             for (int i = lane; i < len; i += 32) {
-                // Sort key: the posting's quantile inside its bank, (2r+1)/(2c) with c = postings of that bank in the
-                // slice, ties broken by bank.  Each bank is thereby spread evenly over the slice, so a window of 32
-                // postings holds ~32*c/len of them (the even share) instead of a run at the slice's tail.
-                // pos = number of postings that sort before this one, in exact integer arithmetic (a permutation).
-                const int r = s_rank[i];
-                const int bank = s_ids[i] & 31;
-                const int c = static_cast<int>(hist[bank]);
-                uint32_t pos = 0;
-                for (int bb = 0; bb < 32; ++bb) {
-                    const int cb = static_cast<int>(hist[bb]);
-                    const int n = (2 * r + 1) * cb - c;    // r' sorts before  <=>  (2r'+1)*c  <(=)  (2r+1)*cb
-                    int cnt;
-                    if (bb < bank) cnt = n < 0 ? 0 : min(cb, n / (2 * c) + 1);        // ties go to the lower bank
-                    else cnt = n <= 0 ? 0 : min(cb, (n + 2 * c - 1) / (2 * c));
-                    pos += static_cast<uint32_t>(cnt);
-                }
+                const uint32_t ks = s_key[i];
+                const uint32_t pos = s_cnt[ks >> 8] + (ks & 0xffu);
                 doc_ids[s_beg + pos] = s_ids[i];
                 weights[s_beg + pos] = s_w[i];
             }
@@ -444,7 +458,7 @@ extern "C" int b200ret_sparse_bank_order(const uint32_t* table, int32_t* doc_ids
     const int32_t n_blocks = (n_docs + block_docs - 1) / block_docs;
     if (n_blocks == 0) return B200RET_OK;
     B200RET_REQUIRE(doc_ids && weights, "sparse_bank_order: null pointer");
-    const size_t smem = static_cast<size_t>(BANK_WARPS) * (BANK_MAX_BLOCK_DOCS * 10 + 128);
+    const size_t smem = static_cast<size_t>(BANK_WARPS) * BANK_WARP_SMEM;
     static bool attr_set = false;
     if (!attr_set) {
         B200RET_CUDA_CHECK(cudaFuncSetAttribute(bank_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

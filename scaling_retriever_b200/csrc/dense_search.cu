@@ -33,6 +33,10 @@ constexpr uint32_t D_TILE_BYTES = 128 * D_BLOCK_K * 2;            // one 128-row
 constexpr uint32_t D_STAGE_BYTES = 2 * D_TILE_BYTES;              // A half + B half per CTA
 constexpr int D_ROUND0_DOCS = 8192;        // first round / safe-schedule round size (candidate capacity = k + this)
 constexpr int D_UNIT_DOCS = D_BLOCK_N;     // round unit = one doc tile
+#ifndef B200RET_DENSE_TILES_PER_PAIR
+#define B200RET_DENSE_TILES_PER_PAIR 256
+#endif
+constexpr int D_MAX_TILES_PER_PAIR = B200RET_DENSE_TILES_PER_PAIR;   // tiles per CTA pair and launch (bounds schedule drift)
 constexpr size_t D_SMEM_BYTES = static_cast<size_t>(D_STAGES) * D_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 struct DenseParams {
@@ -378,17 +382,27 @@ extern "C" int b200ret_dense_search(const void* corpus_bf16, const void* queries
 
     // The safe re-run scores all query blocks again (q_list only narrows the select kernels): rows of queries that did
     // not overflow are recomputed identically, which keeps the GEMM tiling independent of the subset.
+    // A round is cut into launches of at most D_MAX_TILES_PER_PAIR tiles per CTA pair.  The tile schedule inside a launch
+    // is static (pair p takes tiles p, p + #pairs, ...); over a long launch the pairs drift apart, the ~28 pairs that
+    // should share one 256-doc B tile through L2 stop being co-temporal and the corpus is re-read from HBM many times
+    // (measured 13x in a 127 ms launch, none in launches <= 10 ms).  Re-synchronising at launch boundaries bounds the
+    // drift for ~10 us per launch.
+    const int32_t m_blocks = (n_queries + 255) / 256;
+    const int32_t units_per_launch = max(1, (D_MAX_TILES_PER_PAIR * (grid / 2)) / m_blocks);
     auto launch_round = [&](int unit_begin, int unit_end, const int32_t* q_list, int32_t n_active) -> int {
         (void)q_list; (void)n_active;
-        DenseParams r = dp;
-        r.doc_begin = unit_begin * D_UNIT_DOCS;
-        r.doc_end = min(n_docs, unit_end * D_UNIT_DOCS);
-        r.m_blocks = (n_queries + 255) / 256;
-        r.n_tiles = r.m_blocks * (unit_end - unit_begin);
-        prof_begin(PROF_DENSE_GEMM, stream);
-        dense_search_kernel<<<grid, D_THREADS, D_SMEM_BYTES, stream>>>(map_q, map_d, r);
-        prof_end(PROF_DENSE_GEMM, stream);
-        count_launches(1);
+        for (int u = unit_begin; u < unit_end; u += units_per_launch) {
+            const int ue = min(unit_end, u + units_per_launch);
+            DenseParams r = dp;
+            r.doc_begin = u * D_UNIT_DOCS;
+            r.doc_end = min(n_docs, ue * D_UNIT_DOCS);
+            r.m_blocks = m_blocks;
+            r.n_tiles = m_blocks * (ue - u);
+            prof_begin(PROF_DENSE_GEMM, stream);
+            dense_search_kernel<<<grid, D_THREADS, D_SMEM_BYTES, stream>>>(map_q, map_d, r);
+            prof_end(PROF_DENSE_GEMM, stream);
+            count_launches(1);
+        }
         B200RET_CUDA_CHECK(cudaGetLastError());
         return B200RET_OK;
     };

@@ -128,7 +128,7 @@ def test_bank_order_permutes_inside_slices_only(golden, cuda):
             for s0 in range(0, hi - lo, 32):
                 got = np.bincount(b_ids[lo + s0:min(hi, lo + s0 + 32)] & 31, minlength=32)
                 worst = max(worst, int((got - share).max()))
-    assert worst <= 1
+    assert worst <= 2   # integer quantile keys: at most two more than the even share
     keep = ops.SparseDeviceIndex.from_csr(off, ids, w, 40000, bank_order=False)
     assert keep.doc_ids.data_ptr() == ids.data_ptr()
 
