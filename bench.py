@@ -54,21 +54,64 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons sampled DURING the timed region (the fields of the B200_PROFILING.md nvidia-smi recipe).
+    Sampled in-process through NVML (nvidia-ml-py) from a background thread: a polling `nvidia-smi -lms` subprocess was measured
+    to stretch the timed steps by 10-20 % (it re-attaches to the driver on every poll); NVML queries on an open handle do not.
+    Falls back to the nvidia-smi subprocess when the NVML binding is missing."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASON_BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
-    def __init__(self, gpu_index):
-        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
+    def __init__(self, gpu_index, period_s=0.02):
         self.proc = None
+        self.thread = None
+        self.samples = []          # (sm_mhz, reasons bitmask)
+        self.sm_max = None
+        try:
+            import threading
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+            try:
+                handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            self._stop = threading.Event()
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.samples.append((float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)), int(get_reasons(handle))))
+                    except Exception:
+                        pass
+                    self._stop.wait(period_s)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            sm = [s for s, _ in self.samples]
+            if not sm:
+                return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "samples": 0, "via": "nvml"}
+            bits = 0
+            for _, r in self.samples:
+                bits |= r
+            return {"sm_mhz": statistics.median(sm), "sm_max_mhz": self.sm_max,
+                    "reasons": sorted(n for n, b in self.REASON_BITS.items() if bits & b), "samples": len(sm), "via": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         self.proc.terminate()
@@ -149,9 +192,12 @@ def run_b200(args):
     del rows, cols, vals
     torch.cuda.empty_cache()
     t0 = time.perf_counter()
-    index = ops.SparseDeviceIndex.from_csr(term_offsets, doc_ids, weights, hi - lo, copy=False)   # slices bank-ordered in place
+    index = ops.SparseDeviceIndex.from_csr(term_offsets, doc_ids, weights, hi - lo)   # skip table + bank-ordered posting array
     torch.cuda.synchronize()
     table_s = time.perf_counter() - t0
+    index.release_canonical()      # the search only streams index.postings; drop the 8 B/posting canonical copy
+    del doc_ids, weights
+    torch.cuda.empty_cache()
 
     q_off, q_terms, q_w = synth.gen_sparse_queries(n_queries, n_terms=n_terms, device=dev)
     h_off, h_terms, h_w = q_off.cpu().numpy(), q_terms.cpu().numpy(), q_w.cpu().numpy()
@@ -172,7 +218,6 @@ def run_b200(args):
     # nvidia-smi is started BEFORE the warm-up: attaching to the driver stalls the GPU for tens of ms, which must not land
     # in the timed region; the samples it takes during warm-up + timed steps are all under the same load.
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    time.sleep(0.5)
     for _ in range(args.warmup):
         step()
     ops.profile_read(ops.PROF_SPARSE_SCORE)     # drop warm-up records and launch counts
@@ -253,7 +298,10 @@ def run_b200(args):
                   "postings": nnz, "algorithmic_gbs": nnz * 20 / (build_ms / 1e3) / 1e9},
     }
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(term_offsets, doc_ids, weights, n_docs, h_off, h_terms, h_w, out)
+        # the oracle gets the same posting lists the GPU searched (slices in bank order; order inside a list is irrelevant)
+        host = index.postings.cpu()
+        line["cpu_baseline"] = cpu_baseline(term_offsets, host[:, 0].contiguous(), host[:, 1].contiguous().view(torch.float32),
+                                            n_docs, h_off, h_terms, h_w, out)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -325,7 +373,6 @@ def run_b200_dense(args):
 
     ops.profile_enable(True)
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    time.sleep(0.5)
     for _ in range(args.warmup):
         step()
     ops.profile_read(ops.PROF_DENSE_GEMM)

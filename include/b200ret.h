@@ -86,14 +86,17 @@ int b200ret_block_table_build(const int64_t* term_offsets, const int32_t* doc_id
                               int32_t n_terms, int32_t n_docs, int32_t block_docs,
                               uint32_t* table, int32_t* status, void* stream);
 
-/* Search-side layout optimisation, in place, after b200ret_block_table_build: inside every (term, doc
- * block) slice the postings are rewritten in bank-quantile order (bank = doc id mod 32; every bank's
- * postings are spread evenly over the slice), so that 32 consecutive postings hold about the even share
- * 32*c/len of each bank instead of runs, which halves the bank conflicts of the score tile.  The multiset
- * of postings per slice is unchanged (scores are unaffected: a doc occurs once per list); lists are no
- * longer ascending afterwards, so the table must not be rebuilt from the reordered arrays. */
-int b200ret_sparse_bank_order(const uint32_t* table, int32_t* doc_ids, float* weights, int32_t n_terms,
-                              int32_t n_docs, int32_t block_docs, void* stream);
+/* Search-side posting array, after b200ret_block_table_build: postings_out[nnz] holds 8-byte elements
+ * {int32 doc id, fp32 weight} at the SAME positions as the doc-sorted CSR (the skip table addresses both), so
+ * the search kernel fetches a posting with one 64-bit load.  With bank_order != 0 the postings inside every
+ * (term, doc block) slice are additionally permuted into bank-quantile order (bank = doc id mod 32; every
+ * bank's postings spread evenly over the slice): 32 consecutive postings then hold about the even share
+ * 32*c/len of each bank instead of runs, which halves the shared-memory bank conflicts of the score tile.
+ * The multiset of postings per slice is unchanged, so scores are unaffected (a doc occurs once per list).
+ * The canonical CSR arrays are only read. */
+int b200ret_sparse_layout(const uint32_t* table, const int32_t* doc_ids, const float* weights, int64_t nnz,
+                          int32_t n_terms, int32_t n_docs, int32_t block_docs, int bank_order,
+                          void* postings_out, void* stream);
 
 /* Doc-block size (documents per warp-private accumulator tile) compiled into the search kernel. */
 int32_t b200ret_sparse_block_docs(void);
@@ -112,11 +115,12 @@ int32_t b200ret_sparse_block_docs(void);
  * Output per query q (row q of out_scores/out_ids, `k` columns): the out_counts[q] = min(k, #eligible)
  * best docs sorted by (score descending, doc id ascending); unused tail slots hold (-inf, -1).
  * Doc ids are LOCAL row ids + doc_id_base (shard offset for multi-GPU use).
- * `n_docs` is the reference's size_collection.
+ * `n_docs` is the reference's size_collection; `table` / `postings` come from b200ret_block_table_build /
+ * b200ret_sparse_layout.
  * ---------------------------------------------------------------------------------------------- */
 size_t b200ret_sparse_search_workspace_bytes(int32_t n_queries, int32_t k);
 
-int b200ret_sparse_search(const uint32_t* table, const int32_t* doc_ids, const float* weights,
+int b200ret_sparse_search(const uint32_t* table, const void* postings,
                           int32_t n_terms, int32_t n_docs, int32_t block_docs,
                           const int32_t* q_offsets, const int32_t* q_terms, const float* q_weights,
                           int32_t n_queries, int32_t k, float threshold, int64_t doc_id_base,
@@ -127,7 +131,7 @@ int b200ret_sparse_search(const uint32_t* table, const int32_t* doc_ids, const f
  * array inside numba_score_float (indexer.py:332-341) before the threshold filter.
  * out_scores: [n_queries][n_blocks * block_docs] (row stride padded to whole doc blocks; entries past
  * n_docs are 0).  Same kernel, same arithmetic as b200ret_sparse_search.  workspace: >= 256 bytes. */
-int b200ret_sparse_scores(const uint32_t* table, const int32_t* doc_ids, const float* weights,
+int b200ret_sparse_scores(const uint32_t* table, const void* postings,
                           int32_t n_terms, int32_t n_docs, int32_t block_docs,
                           const int32_t* q_offsets, const int32_t* q_terms, const float* q_weights,
                           int32_t n_queries, float* out_scores, void* workspace, size_t workspace_bytes,

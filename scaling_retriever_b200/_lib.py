@@ -28,13 +28,13 @@ PROTOTYPES = {
     "b200ret_csr_build": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i32, _c_i32, _c_int,
                                    _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_sz, _c_ptr]),
     "b200ret_block_table_build": (_c_int, [_c_ptr, _c_ptr, _c_i64, _c_i32, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_ptr]),
-    "b200ret_sparse_bank_order": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_ptr]),
+    "b200ret_sparse_layout": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i32, _c_i32, _c_i32, _c_int, _c_ptr, _c_ptr]),
     "b200ret_sparse_block_docs": (_c_i32, []),
     "b200ret_sparse_search_workspace_bytes": (_c_sz, [_c_i32, _c_i32]),
-    "b200ret_sparse_search": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32,
+    "b200ret_sparse_search": (_c_int, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32,
                                        _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_f32, _c_i64,
                                        _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_sz, _c_ptr]),
-    "b200ret_sparse_scores": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32,
+    "b200ret_sparse_scores": (_c_int, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32,
                                        _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_ptr, _c_ptr, _c_sz, _c_ptr]),
     "b200ret_dense_search_workspace_bytes": (_c_sz, [_c_i32, _c_i32, _c_i32, _c_i32]),
     "b200ret_dense_search": (_c_int, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_i64,

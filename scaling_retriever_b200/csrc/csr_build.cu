@@ -231,26 +231,33 @@ __global__ void block_table_empty_kernel(const int64_t* __restrict__ term_offset
 // [0, len) - its quantile position in the slice; keys of one bank are >= len/c >= 1 apart, so a key value holds at most one
 // posting per bank.  A counting sort over the key values (shared-memory histogram + warp scan) then yields the permutation:
 // one integer division per posting instead of a comparison sort.
-constexpr int BANK_WARPS = 3;
-constexpr int BANK_MAX_BLOCK_DOCS = 4096;
-constexpr int BANK_WARP_SMEM = BANK_MAX_BLOCK_DOCS * 16 + 128;   // ids, weights, (key, slot), key counters + 32 bank counters
+constexpr int BANK_MAX_WARPS = 4;
+constexpr int BANK_MAX_BLOCK_DOCS = 8192;
+// per-warp shared memory for slices of up to `cap` postings: ids, weights, (key, slot), key counters + 32 bank counters
+static inline size_t bank_warp_smem(int cap) { return static_cast<size_t>(cap) * 16 + 128; }
 
-__global__ void __launch_bounds__(BANK_WARPS * 32) bank_order_kernel(const uint32_t* __restrict__ table, int32_t* __restrict__ doc_ids,
-                                                                      float* __restrict__ weights, int32_t n_terms, int32_t n_blocks) {
+// Output: the search-side posting array, (doc id, weight bits) interleaved as 8-byte elements at the SAME positions as the CSR
+// (so the skip table addresses both), every slice bank-ordered when `bank_order` is set, copied as is otherwise.
+__global__ void __launch_bounds__(BANK_MAX_WARPS * 32) posting_layout_kernel(const uint32_t* __restrict__ table,
+                                                                              const int32_t* __restrict__ doc_ids,
+                                                                              const float* __restrict__ weights, uint2* __restrict__ out,
+                                                                              int32_t n_terms, int32_t n_blocks, int32_t cap,
+                                                                              int32_t bank_order) {
     extern __shared__ __align__(16) unsigned char bank_smem[];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
-    unsigned char* mine = bank_smem + static_cast<size_t>(warp) * BANK_WARP_SMEM;
+    const int n_warps = blockDim.x >> 5;
+    unsigned char* mine = bank_smem + static_cast<size_t>(warp) * (static_cast<size_t>(cap) * 16 + 128);
     int32_t* s_ids = reinterpret_cast<int32_t*>(mine);
-    float* s_w = reinterpret_cast<float*>(mine + BANK_MAX_BLOCK_DOCS * 4);
-    uint32_t* s_key = reinterpret_cast<uint32_t*>(mine + BANK_MAX_BLOCK_DOCS * 8);     // pass 1: in-bank rank; pass 2: key << 8 | slot
-    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(mine + BANK_MAX_BLOCK_DOCS * 12);    // postings per key value -> exclusive offsets
-    uint32_t* hist = reinterpret_cast<uint32_t*>(mine + BANK_MAX_BLOCK_DOCS * 16);
+    float* s_w = reinterpret_cast<float*>(mine + static_cast<size_t>(cap) * 4);
+    uint32_t* s_key = reinterpret_cast<uint32_t*>(mine + static_cast<size_t>(cap) * 8);     // pass 1: in-bank rank; pass 2: key << 8 | slot
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(mine + static_cast<size_t>(cap) * 12);    // postings per key value -> exclusive offsets
+    uint32_t* hist = reinterpret_cast<uint32_t*>(mine + static_cast<size_t>(cap) * 16);
     const size_t row_len = static_cast<size_t>(n_blocks) + 1;
     const int groups = (n_blocks + 31) / 32;
     const long long n_items = static_cast<long long>(n_terms) * groups;
-    const long long stride = static_cast<long long>(gridDim.x) * BANK_WARPS;
-    for (long long item = static_cast<long long>(blockIdx.x) * BANK_WARPS + warp; item < n_items; item += stride) {
+    const long long stride = static_cast<long long>(gridDim.x) * n_warps;
+    for (long long item = static_cast<long long>(blockIdx.x) * n_warps + warp; item < n_items; item += stride) {
         const int t = static_cast<int>(item / groups);
         const int b = static_cast<int>(item % groups) * 32 + lane;
         uint32_t beg = 0, end = 0;
@@ -258,12 +265,17 @@ __global__ void __launch_bounds__(BANK_WARPS * 32) bank_order_kernel(const uint3
             beg = table[static_cast<size_t>(t) * row_len + b];
             end = table[static_cast<size_t>(t) * row_len + b + 1];
         }
-        unsigned todo = __ballot_sync(0xffffffffu, end - beg >= 2u && end > beg);
+        unsigned todo = __ballot_sync(0xffffffffu, end > beg);
         while (todo) {
             const int j = __ffs(todo) - 1;
             todo &= todo - 1;
             const uint32_t s_beg = __shfl_sync(0xffffffffu, beg, j);
             const int len = static_cast<int>(__shfl_sync(0xffffffffu, end, j) - s_beg);
+            if (len == 1 || !bank_order) {                     // nothing to reorder: interleave and copy
+                for (int i = lane; i < len; i += 32)
+                    out[s_beg + i] = make_uint2(static_cast<uint32_t>(doc_ids[s_beg + i]), __float_as_uint(weights[s_beg + i]));
+                continue;
+            }
             hist[lane] = 0;
             for (int i = lane; i < len; i += 32) s_cnt[i] = 0;
             __syncwarp();
@@ -298,8 +310,7 @@ __global__ void __launch_bounds__(BANK_WARPS * 32) bank_order_kernel(const uint3
             for (int i = lane; i < len; i += 32) {
                 const uint32_t ks = s_key[i];
                 const uint32_t pos = s_cnt[ks >> 8] + (ks & 0xffu);
-                doc_ids[s_beg + pos] = s_ids[i];
-                weights[s_beg + pos] = s_w[i];
+                out[s_beg + pos] = make_uint2(static_cast<uint32_t>(s_ids[i]), __float_as_uint(s_w[i]));
             }
             __syncwarp();
         }
@@ -449,22 +460,26 @@ extern "C" int b200ret_block_table_build(const int64_t* term_offsets, const int3
     return B200RET_OK;
 }
 
-extern "C" int b200ret_sparse_bank_order(const uint32_t* table, int32_t* doc_ids, float* weights, int32_t n_terms,
-                                         int32_t n_docs, int32_t block_docs, void* stream_) {
+extern "C" int b200ret_sparse_layout(const uint32_t* table, const int32_t* doc_ids, const float* weights, int64_t nnz,
+                                     int32_t n_terms, int32_t n_docs, int32_t block_docs, int bank_order, void* postings_out,
+                                     void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    B200RET_REQUIRE(table && n_terms > 0 && n_docs >= 0, "sparse_bank_order: bad arguments");
+    B200RET_REQUIRE(table && n_terms > 0 && n_docs >= 0 && nnz >= 0, "sparse_layout: bad arguments");
     B200RET_REQUIRE(block_docs > 0 && block_docs <= BANK_MAX_BLOCK_DOCS && block_docs % 32 == 0,
-                    "sparse_bank_order: block_docs=%d must be a multiple of 32 and <= %d", block_docs, BANK_MAX_BLOCK_DOCS);
+                    "sparse_layout: block_docs=%d must be a multiple of 32 and <= %d", block_docs, BANK_MAX_BLOCK_DOCS);
     const int32_t n_blocks = (n_docs + block_docs - 1) / block_docs;
-    if (n_blocks == 0) return B200RET_OK;
-    B200RET_REQUIRE(doc_ids && weights, "sparse_bank_order: null pointer");
-    const size_t smem = static_cast<size_t>(BANK_WARPS) * BANK_WARP_SMEM;
+    if (n_blocks == 0 || nnz == 0) return B200RET_OK;
+    B200RET_REQUIRE(doc_ids && weights && postings_out, "sparse_layout: null pointer");
+    B200RET_REQUIRE(reinterpret_cast<uintptr_t>(postings_out) % 8 == 0, "sparse_layout: postings_out must be 8-byte aligned");
+    const int warps = max(1, min(BANK_MAX_WARPS, static_cast<int>((220 * 1024) / bank_warp_smem(block_docs))));
+    const size_t smem = static_cast<size_t>(warps) * bank_warp_smem(block_docs);
     static bool attr_set = false;
     if (!attr_set) {
-        B200RET_CUDA_CHECK(cudaFuncSetAttribute(bank_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        B200RET_CUDA_CHECK(cudaFuncSetAttribute(posting_layout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         attr_set = true;
     }
-    bank_order_kernel<<<sm_count(), BANK_WARPS * 32, smem, stream>>>(table, doc_ids, weights, n_terms, n_blocks);
+    posting_layout_kernel<<<sm_count(), warps * 32, smem, stream>>>(table, doc_ids, weights, static_cast<uint2*>(postings_out),
+                                                                   n_terms, n_blocks, block_docs, bank_order);
     count_launches(1);
     B200RET_CUDA_CHECK(cudaGetLastError());
     return B200RET_OK;

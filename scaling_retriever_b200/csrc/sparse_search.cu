@@ -27,8 +27,13 @@
 
 namespace b200ret {
 
-constexpr int ROUND0_BLOCKS = 4;       // first round / safe-schedule round size, in doc blocks
-#ifndef B200RET_LDNC            // posting-load flavour (tuning knob)
+#ifndef B200RET_SCORE_WARPS     // kernel shape (tuning knobs): warps per CTA, docs per warp tile, blocks in round 0
+#define B200RET_SCORE_WARPS 16
+#define B200RET_BLOCK_DOCS 3456
+#define B200RET_ROUND0_BLOCKS 4
+#endif
+constexpr int ROUND0_BLOCKS = B200RET_ROUND0_BLOCKS;   // first round / safe-schedule round size, in doc blocks
+#ifndef B200RET_LDNC           // posting-load flavour (tuning knob)
 #define B200RET_LDNC "ld.global.nc"
 #endif
 #ifndef B200RET_LOOKAHEAD       // prefetch the next term group's skip-table entries (tuning knob)
@@ -44,8 +49,8 @@ constexpr int STEP_ROWS = B200RET_STEP_ROWS;     // rows (of 32 postings) fetche
 constexpr int PIPE_DEPTH = B200RET_PIPE_DEPTH;   // steps in flight per warp (register ring)
 
 // Kernel shape: one CTA of WARPS warps per SM, BD docs per warp-private score tile (BD * 4 bytes of shared memory).
-constexpr int SCORE_WARPS = 16;
-constexpr int BLOCK_DOCS = 3456;       // 16 warps x (13.5 KB scores + 384 B slice descriptors) = 222 KB of the 227 KB
+constexpr int SCORE_WARPS = B200RET_SCORE_WARPS;
+constexpr int BLOCK_DOCS = B200RET_BLOCK_DOCS;   // default: 16 warps x (13.5 KB scores + 384 B slice descriptors) = 222 KB of 227 KB
 constexpr int SCORE_THREADS = SCORE_WARPS * 32;
 constexpr size_t SCORE_SMEM = static_cast<size_t>(SCORE_WARPS) * (BLOCK_DOCS * sizeof(float) + 3 * 32 * sizeof(uint32_t));
 static_assert(BLOCK_DOCS % 128 == 0, "tile sweep uses 128-bit accesses by 32 lanes");
@@ -54,8 +59,7 @@ static_assert(SCORE_SMEM <= 227 * 1024, "exceeds the shared memory of one SM");
 struct ScoreParams {
     const uint32_t* table;     // [n_terms][table_stride]
     size_t table_stride;       // n_blocks + 1
-    const int32_t* doc_ids;
-    const float* weights;
+    const uint2* postings;     // [nnz] {doc id, weight bits}, CSR positions (b200ret_sparse_layout)
     const int32_t* q_offsets;
     const int32_t* q_terms;
     const float* q_weights;
@@ -81,8 +85,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const Sc
     float* const acc = smem_acc + warp * BD;
     // warp-private slice descriptors of the current term group: beg[32], end[32], query weight[32]
     uint32_t* const desc = reinterpret_cast<uint32_t*>(smem_acc + SCORE_WARPS * BD) + warp * 96;
-    const int32_t* __restrict__ const g_ids = p.doc_ids + lane;     // lane-private bases: address = base + row position
-    const float* __restrict__ const g_w = p.weights + lane;
+    const uint2* __restrict__ const g_post = p.postings + lane;     // lane-private base: address = base + row position
     const uint32_t* __restrict__ const g_table = p.table;
     const size_t table_stride = p.table_stride;
     const int n_active = p.n_active;
@@ -171,8 +174,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const Sc
                 qw = c_qw;
                 rel = c_row + lane - c_beg;
                 len = more ? c_end - c_beg : 0u;
-                const int32_t* ids_row = g_ids + c_row;     // one 64-bit address per array and step; rows use immediates
-                const float* w_row = g_w + c_row;
+                const uint2* row0 = g_post + c_row;   // one 64-bit address per step; rows are 256 bytes apart (immediates)
                 asm volatile(
                     "{\n\t"
                     ".reg .pred p0, p1, p2, p3;\n\t"
@@ -184,17 +186,13 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const Sc
                     "setp.lt.u32 p1, t1, %9;\n\t"
                     "setp.lt.u32 p2, t2, %9;\n\t"
                     "setp.lt.u32 p3, t3, %9;\n\t"
-                    "@p0 " B200RET_LDNC ".u32 %0, [%10];\n\t"
-                    "@p0 " B200RET_LDNC ".f32 %4, [%11];\n\t"
-                    "@p1 " B200RET_LDNC ".u32 %1, [%10 + 128];\n\t"
-                    "@p1 " B200RET_LDNC ".f32 %5, [%11 + 128];\n\t"
-                    "@p2 " B200RET_LDNC ".u32 %2, [%10 + 256];\n\t"
-                    "@p2 " B200RET_LDNC ".f32 %6, [%11 + 256];\n\t"
-                    "@p3 " B200RET_LDNC ".u32 %3, [%10 + 384];\n\t"
-                    "@p3 " B200RET_LDNC ".f32 %7, [%11 + 384];\n\t"
+                    "@p0 " B200RET_LDNC ".v2.b32 {%0, %4}, [%10];\n\t"          // one posting = {doc id, weight bits}
+                    "@p1 " B200RET_LDNC ".v2.b32 {%1, %5}, [%10 + 256];\n\t"
+                    "@p2 " B200RET_LDNC ".v2.b32 {%2, %6}, [%10 + 512];\n\t"
+                    "@p3 " B200RET_LDNC ".v2.b32 {%3, %7}, [%10 + 768];\n\t"
                     "}\n"
                     : "=r"(id[0]), "=r"(id[1]), "=r"(id[2]), "=r"(id[3]), "=f"(w[0]), "=f"(w[1]), "=f"(w[2]), "=f"(w[3])
-                    : "r"(rel), "r"(len), "l"(ids_row), "l"(w_row));
+                    : "r"(rel), "r"(len), "l"(row0));
                 c_row += 32u * R;
                 return more;
             };
@@ -335,7 +333,7 @@ extern "C" size_t b200ret_sparse_search_workspace_bytes(int32_t n_queries, int32
     return carve_cand(ws, n_queries, search_cap(k), nullptr) + 256;
 }
 
-static int fill_params(ScoreParams& sp, const uint32_t* table, const int32_t* doc_ids, const float* weights, int32_t n_docs,
+static int fill_params(ScoreParams& sp, const uint32_t* table, const void* postings, int32_t n_docs,
                        int32_t block_docs, const int32_t* q_offsets, const int32_t* q_terms, const float* q_weights,
                        int32_t n_queries) {
     const int bd = block_docs_of_shape();
@@ -344,8 +342,7 @@ static int fill_params(ScoreParams& sp, const uint32_t* table, const int32_t* do
     sp = ScoreParams{};
     sp.table = table;
     sp.table_stride = static_cast<size_t>(n_blocks) + 1;
-    sp.doc_ids = doc_ids;
-    sp.weights = weights;
+    sp.postings = static_cast<const uint2*>(postings);
     sp.q_offsets = q_offsets;
     sp.q_terms = q_terms;
     sp.q_weights = q_weights;
@@ -354,7 +351,7 @@ static int fill_params(ScoreParams& sp, const uint32_t* table, const int32_t* do
     return B200RET_OK;
 }
 
-extern "C" int b200ret_sparse_scores(const uint32_t* table, const int32_t* doc_ids, const float* weights,
+extern "C" int b200ret_sparse_scores(const uint32_t* table, const void* postings,
                                      int32_t n_terms, int32_t n_docs, int32_t block_docs,
                                      const int32_t* q_offsets, const int32_t* q_terms, const float* q_weights,
                                      int32_t n_queries, float* out_scores, void* workspace, size_t workspace_bytes,
@@ -362,7 +359,7 @@ extern "C" int b200ret_sparse_scores(const uint32_t* table, const int32_t* doc_i
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     B200RET_REQUIRE(n_queries >= 0 && n_docs >= 0 && n_terms > 0, "sparse_scores: bad sizes");
     ScoreParams sp;
-    int rc = fill_params(sp, table, doc_ids, weights, n_docs, block_docs, q_offsets, q_terms, q_weights, n_queries);
+    int rc = fill_params(sp, table, postings, n_docs, block_docs, q_offsets, q_terms, q_weights, n_queries);
     if (rc != B200RET_OK) return rc;
     if (n_queries == 0 || n_docs == 0) return B200RET_OK;
     B200RET_REQUIRE(table && q_offsets && out_scores && workspace && workspace_bytes >= 256, "sparse_scores: null pointer / workspace < 256 B");
@@ -375,7 +372,7 @@ extern "C" int b200ret_sparse_scores(const uint32_t* table, const int32_t* doc_i
     return launch_score(sp, stream);
 }
 
-extern "C" int b200ret_sparse_search(const uint32_t* table, const int32_t* doc_ids, const float* weights,
+extern "C" int b200ret_sparse_search(const uint32_t* table, const void* postings,
                                      int32_t n_terms, int32_t n_docs, int32_t block_docs,
                                      const int32_t* q_offsets, const int32_t* q_terms, const float* q_weights,
                                      int32_t n_queries, int32_t k, float threshold, int64_t doc_id_base,
@@ -383,7 +380,7 @@ extern "C" int b200ret_sparse_search(const uint32_t* table, const int32_t* doc_i
                                      void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     ScoreParams sp;
-    int rc = fill_params(sp, table, doc_ids, weights, n_docs, block_docs, q_offsets, q_terms, q_weights, n_queries);
+    int rc = fill_params(sp, table, postings, n_docs, block_docs, q_offsets, q_terms, q_weights, n_queries);
     if (rc != B200RET_OK) return rc;
     B200RET_REQUIRE(k >= 1 && k <= B200RET_MAX_K, "sparse_search: k=%d outside [1, %d]", k, B200RET_MAX_K);
     B200RET_REQUIRE(n_queries >= 0 && n_docs >= 0 && n_terms > 0, "sparse_search: bad sizes");

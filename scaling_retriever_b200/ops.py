@@ -102,42 +102,53 @@ def block_table_build(term_offsets, doc_ids, n_docs, blk_docs=None):
 
 @dataclass
 class SparseDeviceIndex:
-    """A doc-sorted CSR posting-list index resident in HBM plus its doc-block skip table."""
+    """A doc-sorted CSR posting-list index resident in HBM: the canonical CSR (term_offsets, doc_ids, weights — bit-identical
+    to the reference's per-term arrays), the doc-block skip table, and the search-side posting array the kernel streams
+    ({doc id, weight} interleaved as 8-byte elements at the CSR positions, every (term, doc block) slice bank-ordered)."""
     term_offsets: torch.Tensor   # int64 [n_terms + 1]
-    doc_ids: torch.Tensor        # int32 [nnz], ascending inside each term
-    weights: torch.Tensor        # fp32 [nnz]
+    doc_ids: torch.Tensor        # int32 [nnz], ascending inside each term (None after release_canonical)
+    weights: torch.Tensor        # fp32 [nnz] (None after release_canonical)
     table: torch.Tensor          # int32 storage of uint32 [n_terms, n_blocks + 1]
+    postings: torch.Tensor       # int32 [nnz, 2]: column 0 doc id, column 1 fp32 weight bits
     n_terms: int
     n_docs: int
     block_docs: int
 
     @property
     def nnz(self):
-        return self.doc_ids.numel()
+        return self.postings.shape[0]
 
     @property
     def device(self):
-        return self.doc_ids.device
+        return self.postings.device
+
+    def release_canonical(self):
+        """Drop the canonical doc_ids/weights arrays (8 B/posting) once nothing needs to export them."""
+        self.doc_ids = None
+        self.weights = None
+
+    def csr_arrays(self):
+        """(term_offsets, doc_ids, weights) with lists in search order (a per-slice permutation of the canonical CSR)."""
+        p = self.postings
+        return self.term_offsets, p[:, 0].contiguous(), p[:, 1].contiguous().view(torch.float32)
 
     @classmethod
-    def from_csr(cls, term_offsets, doc_ids, weights, n_docs, bank_order=True, copy=True):
-        """Wrap a doc-sorted CSR.  `bank_order` rewrites every (term, doc block) slice in shared-memory-bank order for
-        the search kernel; with `copy` (default) that happens on clones so the caller's canonical CSR stays intact."""
+    def from_csr(cls, term_offsets, doc_ids, weights, n_docs, bank_order=True):
+        """Wrap a doc-sorted CSR: build the skip table and the search-side posting array (the CSR itself is only read)."""
         table = block_table_build(term_offsets, doc_ids, n_docs)
         n_terms = term_offsets.numel() - 1
-        if bank_order and doc_ids.numel():
-            if copy:
-                doc_ids, weights = doc_ids.clone(), weights.clone()
-            with torch.cuda.device(doc_ids.device):
-                _lib.check(_lib.load().b200ret_sparse_bank_order(_ptr(table), _ptr(doc_ids), _ptr(weights), n_terms, int(n_docs),
-                                                                 block_docs(), _stream()))
-        return cls(term_offsets, doc_ids, weights, table, n_terms, int(n_docs), block_docs())
+        nnz = doc_ids.numel()
+        postings = torch.empty((nnz, 2), dtype=torch.int32, device=doc_ids.device)
+        with torch.cuda.device(doc_ids.device):
+            _lib.check(_lib.load().b200ret_sparse_layout(_ptr(table), _ptr(doc_ids), _ptr(weights), nnz, n_terms, int(n_docs),
+                                                         block_docs(), int(bool(bank_order)), _ptr(postings), _stream()))
+        return cls(term_offsets, doc_ids, weights, table, postings, n_terms, int(n_docs), block_docs())
 
     @classmethod
     def from_coo(cls, rows, cols, vals, n_terms, n_docs):
         """Build from COO postings in any order (lists come out ascending in doc id)."""
         term_offsets, doc_ids, weights = csr_build(rows, cols, vals, n_terms, n_docs, sort_docs=True)
-        return cls.from_csr(term_offsets, doc_ids, weights, n_docs, copy=False)
+        return cls.from_csr(term_offsets, doc_ids, weights, n_docs)
 
 
 def sparse_search(index, q_offsets, q_terms, q_weights, k, threshold=0.0, doc_id_base=0):
@@ -158,7 +169,7 @@ def sparse_search(index, q_offsets, q_terms, q_weights, k, threshold=0.0, doc_id
         ws_bytes = lib.b200ret_sparse_search_workspace_bytes(n_queries, k)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         _lib.check(lib.b200ret_sparse_search(
-            _ptr(index.table), _ptr(index.doc_ids), _ptr(index.weights), index.n_terms, index.n_docs, index.block_docs,
+            _ptr(index.table), _ptr(index.postings), index.n_terms, index.n_docs, index.block_docs,
             _ptr(q_offsets), _ptr(q_terms), _ptr(q_weights), n_queries, k, float(threshold), int(doc_id_base),
             _ptr(out_scores), _ptr(out_ids), _ptr(out_counts), _ptr(ws), ws_bytes, _stream()))
     return out_scores, out_ids, out_counts
@@ -177,7 +188,7 @@ def sparse_scores(index, q_offsets, q_terms, q_weights):
         out = torch.zeros((n_queries, n_blocks * index.block_docs), dtype=torch.float32, device=dev)
         ws = torch.empty(256, dtype=torch.uint8, device=dev)
         _lib.check(lib.b200ret_sparse_scores(
-            _ptr(index.table), _ptr(index.doc_ids), _ptr(index.weights), index.n_terms, index.n_docs, index.block_docs,
+            _ptr(index.table), _ptr(index.postings), index.n_terms, index.n_docs, index.block_docs,
             _ptr(q_offsets), _ptr(q_terms), _ptr(q_weights), n_queries, _ptr(out), _ptr(ws), 256, _stream()))
     return out[:, :index.n_docs]
 

@@ -49,9 +49,9 @@ def test_non_compute_entry_points_work_without_gpu():
 
 def test_argument_validation_reports_errors_without_touching_the_gpu():
     lib = _lib.load()
-    rc = lib.b200ret_sparse_search(None, None, None, 10, 10, 1, None, None, None, 1, 10, 0.0, 0, None, None, None, None, 0, None)
+    rc = lib.b200ret_sparse_search(None, None, 10, 10, 1, None, None, None, 1, 10, 0.0, 0, None, None, None, None, 0, None)
     assert rc == -1 and b"block_docs" in lib.b200ret_last_error()
-    rc = lib.b200ret_sparse_search(None, None, None, 10, 10, lib.b200ret_sparse_block_docs(), None, None, None, 1, 100000, 0.0, 0,
+    rc = lib.b200ret_sparse_search(None, None, 10, 10, lib.b200ret_sparse_block_docs(), None, None, None, 1, 100000, 0.0, 0,
                                    None, None, None, None, 0, None)
     assert rc == -1 and b"k=" in lib.b200ret_last_error()
     with pytest.raises(_lib.B200RetError):

@@ -105,17 +105,18 @@ def test_block_table_rejects_unsorted_lists(golden, cuda):
     assert err.value.code == -4
 
 
-def test_bank_order_permutes_inside_slices_only(golden, cuda):
-    """b200ret_sparse_bank_order: every (term, doc block) slice keeps its multiset of (doc, weight) postings, and a window
-    of 32 consecutive postings holds at most one more than the even share ceil(32*c/len) of any shared-memory bank
-    (doc % 32, c = postings of that bank in the slice)."""
+def test_posting_layout_permutes_inside_slices_only(golden, cuda):
+    """b200ret_sparse_layout: the search-side {doc, weight} array keeps every (term, doc block) slice's multiset of postings
+    at the CSR positions, leaves the canonical CSR untouched, and with bank_order a window of 32 consecutive postings holds
+    at most two more than the even share ceil(32*c/len) of any shared-memory bank (doc % 32, c = postings of that bank)."""
     rows, cols, vals = synth.gen_sparse_docs(40000, n_terms=300, mean_nnz=40, seed=13, device=cuda)
     off, ids, w = ops.csr_build(rows, cols, vals, 300, 40000)
-    index = ops.SparseDeviceIndex.from_csr(off, ids, w, 40000)            # bank-ordered copy
-    assert index.doc_ids.data_ptr() != ids.data_ptr()
-    table = index.table.cpu().numpy().view(np.uint32)
     a_ids, a_w = ids.cpu().numpy(), w.cpu().numpy()
-    b_ids, b_w = index.doc_ids.cpu().numpy(), index.weights.cpu().numpy()
+    index = ops.SparseDeviceIndex.from_csr(off, ids, w, 40000)
+    assert index.doc_ids.data_ptr() == ids.data_ptr() and np.array_equal(ids.cpu().numpy(), a_ids)   # canonical CSR only read
+    table = index.table.cpu().numpy().view(np.uint32)
+    _, p_ids, p_w = index.csr_arrays()
+    b_ids, b_w = p_ids.cpu().numpy(), p_w.cpu().numpy()
     worst = 0
     for t in range(0, 300, 7):
         for b in range(table.shape[1] - 1):
@@ -129,8 +130,9 @@ def test_bank_order_permutes_inside_slices_only(golden, cuda):
                 got = np.bincount(b_ids[lo + s0:min(hi, lo + s0 + 32)] & 31, minlength=32)
                 worst = max(worst, int((got - share).max()))
     assert worst <= 2   # integer quantile keys: at most two more than the even share
-    keep = ops.SparseDeviceIndex.from_csr(off, ids, w, 40000, bank_order=False)
-    assert keep.doc_ids.data_ptr() == ids.data_ptr()
+    plain = ops.SparseDeviceIndex.from_csr(off, ids, w, 40000, bank_order=False)      # interleave only: CSR order kept
+    _, q_ids, q_w = plain.csr_arrays()
+    assert torch.equal(q_ids, ids) and torch.equal(q_w, w)
 
 
 # ---------------------------------------------------------------------------------------------------- scoring
