@@ -39,6 +39,12 @@ constexpr int ROUND0_BLOCKS = B200RET_ROUND0_BLOCKS;   // first round / safe-sch
 #ifndef B200RET_LOOKAHEAD       // prefetch the next term group's skip-table entries (tuning knob)
 #define B200RET_LOOKAHEAD 1
 #endif
+#ifndef B200RET_FUSED_STEP      // issue step f's posting loads inside step s's accumulate block (tuning knob)
+#define B200RET_FUSED_STEP 0     // measured equal to the separate blocks (129.8 vs 129.5 ms per 6,980-query step)
+#endif
+#ifndef B200RET_SHORT_STEP      // one-row code path for steps whose slice ends inside row 0 (tuning knob)
+#define B200RET_SHORT_STEP 0     // measured SLOWER (138.7 vs 128.7 ms): the warp-uniform branch costs more than the dead slots
+#endif
 #ifndef B200RET_STEP_ROWS
 #define B200RET_STEP_ROWS 4
 #endif
@@ -157,7 +163,8 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const Sc
             // A step's liveness is (rel + 32*row < len) per lane: rel = position of the lane in row 0 relative to the
             // slice begin (wraps to a huge value before the slice), len = slice length (0 = empty step).  The loads leave
             // dead lanes' registers unwritten (no initialisation moves); consume() re-derives the same predicates.
-            auto fetch = [&](int (&id)[R], float (&w)[R], float& qw, unsigned& rel, unsigned& len) -> bool {
+            // advance(): the warp-uniform cursor logic of one step (no memory traffic except 3 LDS at a slice change)
+            auto advance = [&](float& qw, unsigned& rel, unsigned& len, const uint2*& row0) -> bool {
                 bool more = true;
                 if (c_row >= c_end) {                      // warp-uniform: current slice exhausted
                     if (pending != 0) {
@@ -174,7 +181,28 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const Sc
                 qw = c_qw;
                 rel = c_row + lane - c_beg;
                 len = more ? c_end - c_beg : 0u;
-                const uint2* row0 = g_post + c_row;   // one 64-bit address per step; rows are 256 bytes apart (immediates)
+                row0 = g_post + c_row;                // one 64-bit address per step; rows are 256 bytes apart (immediates)
+                c_row += 32u * R;
+                return more;
+            };
+            auto fetch = [&](int (&id)[R], float (&w)[R], float& qw, unsigned& rel, unsigned& len) -> bool {
+                const uint2* row0;
+                const bool more = advance(qw, rel, len, row0);
+#if B200RET_SHORT_STEP
+                // Half of the query terms are rare: their slice is a handful of postings inside row 0.  A warp-uniform branch
+                // keeps the three dead rows' loads out of the L1 data pipe (a fully predicated-off load still takes a slot).
+                if (static_cast<int>(rel - lane) + 32 >= static_cast<int>(len)) {
+                    asm volatile(
+                        "{\n\t"
+                        ".reg .pred p0;\n\t"
+                        "setp.lt.u32 p0, %2, %3;\n\t"
+                        "@p0 " B200RET_LDNC ".v2.b32 {%0, %1}, [%4];\n\t"
+                        "}\n"
+                        : "=r"(id[0]), "=f"(w[0])
+                        : "r"(rel), "r"(len), "l"(row0));
+                    return more;
+                }
+#endif
                 asm volatile(
                     "{\n\t"
                     ".reg .pred p0, p1, p2, p3;\n\t"
@@ -193,8 +221,61 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const Sc
                     "}\n"
                     : "=r"(id[0]), "=r"(id[1]), "=r"(id[2]), "=r"(id[3]), "=f"(w[0]), "=f"(w[1]), "=f"(w[2]), "=f"(w[3])
                     : "r"(rel), "r"(len), "l"(row0));
-                c_row += 32u * R;
                 return more;
+            };
+            // fused(): accumulate step s AND issue the loads of step f in one instruction block, so the posting loads and
+            // their predicate arithmetic fill the shared-memory load latency of the accumulate (LDS -> FADD -> STS).
+            auto fused = [&](const int (&id)[R], const float (&w)[R], float qw, unsigned rel, unsigned len,
+                             int (&fid)[R], float (&fw)[R], unsigned frel, unsigned flen, const uint2* frow0) {
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred p0, p1, p2, p3, q0, q1, q2, q3;\n\t"
+                    ".reg .f32 a0, a1, a2, a3, v0, v1, v2, v3;\n\t"
+                    ".reg .u32 d0, d1, d2, d3, t1, t2, t3, u1, u2, u3;\n\t"
+                    "add.u32 t1, %17, 32;\n\t"
+                    "add.u32 t2, %17, 64;\n\t"
+                    "add.u32 t3, %17, 96;\n\t"
+                    "setp.lt.u32 p0, %17, %18;\n\t"
+                    "setp.lt.u32 p1, t1, %18;\n\t"
+                    "setp.lt.u32 p2, t2, %18;\n\t"
+                    "setp.lt.u32 p3, t3, %18;\n\t"
+                    "mad.lo.u32 d0, %8, 4, %19;\n\t"
+                    "mad.lo.u32 d1, %9, 4, %19;\n\t"
+                    "mad.lo.u32 d2, %10, 4, %19;\n\t"
+                    "mad.lo.u32 d3, %11, 4, %19;\n\t"
+                    "@p0 ld.shared.f32 a0, [d0];\n\t"
+                    "@p1 ld.shared.f32 a1, [d1];\n\t"
+                    "@p2 ld.shared.f32 a2, [d2];\n\t"
+                    "@p3 ld.shared.f32 a3, [d3];\n\t"
+                    "add.u32 u1, %20, 32;\n\t"
+                    "add.u32 u2, %20, 64;\n\t"
+                    "add.u32 u3, %20, 96;\n\t"
+                    "setp.lt.u32 q0, %20, %21;\n\t"
+                    "setp.lt.u32 q1, u1, %21;\n\t"
+                    "setp.lt.u32 q2, u2, %21;\n\t"
+                    "setp.lt.u32 q3, u3, %21;\n\t"
+                    "@q0 " B200RET_LDNC ".v2.b32 {%0, %4}, [%22];\n\t"
+                    "@q1 " B200RET_LDNC ".v2.b32 {%1, %5}, [%22 + 256];\n\t"
+                    "@q2 " B200RET_LDNC ".v2.b32 {%2, %6}, [%22 + 512];\n\t"
+                    "@q3 " B200RET_LDNC ".v2.b32 {%3, %7}, [%22 + 768];\n\t"
+                    "mul.rn.f32 v0, %16, %12;\n\t"
+                    "mul.rn.f32 v1, %16, %13;\n\t"
+                    "mul.rn.f32 v2, %16, %14;\n\t"
+                    "mul.rn.f32 v3, %16, %15;\n\t"
+                    "@p0 add.rn.f32 a0, a0, v0;\n\t"
+                    "@p1 add.rn.f32 a1, a1, v1;\n\t"
+                    "@p2 add.rn.f32 a2, a2, v2;\n\t"
+                    "@p3 add.rn.f32 a3, a3, v3;\n\t"
+                    "@p0 st.shared.f32 [d0], a0;\n\t"
+                    "@p1 st.shared.f32 [d1], a1;\n\t"
+                    "@p2 st.shared.f32 [d2], a2;\n\t"
+                    "@p3 st.shared.f32 [d3], a3;\n\t"
+                    "}\n"
+                    : "=&r"(fid[0]), "=&r"(fid[1]), "=&r"(fid[2]), "=&r"(fid[3]), "=&f"(fw[0]), "=&f"(fw[1]), "=&f"(fw[2]), "=&f"(fw[3])
+                    : "r"(id[0]), "r"(id[1]), "r"(id[2]), "r"(id[3]), "f"(w[0]), "f"(w[1]), "f"(w[2]), "f"(w[3]), "f"(qw), "r"(rel),
+                      "r"(len), "r"(acc_rel_s), "r"(frel), "r"(flen), "l"(frow0)
+                    : "memory");
+                __syncwarp();   // orders this step's shared-memory updates before the next step (possibly the next term)
             };
             // Accumulate one step.  Its rows belong to ONE posting list, so their doc ids are distinct and the R
             // read-modify-writes are independent: loads, adds and stores are issued R-wide (one latency per step).
@@ -202,6 +283,25 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const Sc
             // (id < 0) are predicated off.
             auto consume = [&](const int (&id)[R], const float (&w)[R], float qw, unsigned rel, unsigned len) {
                 static_assert(R == 4, "the fetch/accumulate blocks are written for 4 rows per step");
+#if B200RET_SHORT_STEP
+                if (static_cast<int>(rel - lane) + 32 >= static_cast<int>(len)) {   // same warp-uniform test as in fetch()
+                    asm volatile(
+                        "{\n\t"
+                        ".reg .pred p0;\n\t"
+                        ".reg .f32 a0, v0;\n\t"
+                        ".reg .u32 d0;\n\t"
+                        "setp.lt.u32 p0, %3, %4;\n\t"
+                        "mad.lo.u32 d0, %0, 4, %5;\n\t"
+                        "@p0 ld.shared.f32 a0, [d0];\n\t"
+                        "mul.rn.f32 v0, %2, %1;\n\t"
+                        "@p0 add.rn.f32 a0, a0, v0;\n\t"
+                        "@p0 st.shared.f32 [d0], a0;\n\t"
+                        "}\n" ::"r"(id[0]), "f"(w[0]), "f"(qw), "r"(rel), "r"(len), "r"(acc_rel_s)
+                        : "memory");
+                    __syncwarp();
+                    return;
+                }
+#endif
                 asm volatile(
                     "{\n\t"
                     ".reg .pred p0, p1, p2, p3;\n\t"
@@ -254,12 +354,22 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const Sc
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                     const int f = (s + S - 1) % S;                 // slot freed by the previous consume
+#if B200RET_FUSED_STEP
+                    const uint2* frow0;
+                    more[f] = advance(qw[f], rel[f], len[f], frow0);
+                    if (!more[s]) {                                // oldest step is empty: nothing is left at all
+                        running = false;
+                        break;
+                    }
+                    fused(id[s], w[s], qw[s], rel[s], len[s], id[f], w[f], rel[f], len[f], frow0);
+#else
                     more[f] = fetch(id[f], w[f], qw[f], rel[f], len[f]);
                     if (!more[s]) {                                // oldest step is empty: nothing is left at all
                         running = false;
                         break;
                     }
                     consume(id[s], w[s], qw[s], rel[s], len[s]);
+#endif
                 }
             }
             __syncwarp();   // the descriptors are rewritten by the next term group
