@@ -18,7 +18,11 @@ constexpr int SORT_THREADS = 512;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_ROUNDS = 8;                                  // postings per lane per tile
 constexpr int SORT_TILE = SORT_THREADS * SORT_ROUNDS;           // 4096 postings per tile
-constexpr int SORT_MAX_BUCKETS = 256;
+#ifndef B200RET_SORT_BITS
+#define B200RET_SORT_BITS 9       // digit width per pass: 17-bit term ids sort in 2 passes (9 + 8)
+#endif
+constexpr int SORT_MAX_BITS = B200RET_SORT_BITS;
+constexpr int SORT_MAX_BUCKETS = 1 << SORT_MAX_BITS;
 
 struct SortPass {
     const int32_t* src_row;
@@ -48,12 +52,17 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(SortPass p, int
     const int64_t hi = min(nnz, lo + per_block);
     const int32_t* keys = p.key_is_row ? p.src_row : p.src_col;
     const uint32_t mask = (1u << p.bits) - 1u;
-    for (int64_t i = lo + threadIdx.x; i < hi; i += SORT_THREADS) {
-        uint32_t d = (static_cast<uint32_t>(__ldg(keys + i)) >> p.shift) & mask;
-        // Warp-aggregate equal digits before touching shared memory (Zipfian term ids collide a lot).
-        unsigned peers = __match_any_sync(__activemask(), d);
-        if ((peers & lanemask_lt()) == 0) atomicAdd(&hist[d], __popc(peers));
+    // 8 independent loads per thread in flight (the loop is bandwidth work; one load per iteration left it latency-bound)
+    constexpr int U = 8;
+    int64_t i = lo + threadIdx.x;
+    for (; i + static_cast<int64_t>(U - 1) * SORT_THREADS < hi; i += static_cast<int64_t>(U) * SORT_THREADS) {
+        uint32_t k[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) k[u] = static_cast<uint32_t>(__ldg(keys + i + static_cast<int64_t>(u) * SORT_THREADS));
+#pragma unroll
+        for (int u = 0; u < U; ++u) atomicAdd(&hist[(k[u] >> p.shift) & mask], 1u);
     }
+    for (; i < hi; i += SORT_THREADS) atomicAdd(&hist[(static_cast<uint32_t>(__ldg(keys + i)) >> p.shift) & mask], 1u);
     __syncthreads();
     for (int i = threadIdx.x; i < buckets; i += SORT_THREADS) counts[static_cast<size_t>(i) * gridDim.x + blockIdx.x] = hist[i];
 }
@@ -83,7 +92,7 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(uint32_t* __restrict__ 
     }
 }
 
-__global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(SortPass p, int64_t nnz, int64_t per_block,
+__global__ void __launch_bounds__(SORT_THREADS, 2) sort_scatter_kernel(SortPass p, int64_t nnz, int64_t per_block,
                                                                     const uint32_t* __restrict__ bases) {
     __shared__ uint32_t wcnt[SORT_WARPS][SORT_MAX_BUCKETS];
     __shared__ uint32_t gbase[SORT_MAX_BUCKETS];
@@ -116,7 +125,14 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(SortPass p, 
             const bool valid = (wbase + r * 32 + lane) < hi;
             const uint32_t d = valid ? pass_digit(p, row[r], col[r]) : 0xffffffffu;
             dig[r] = d;
-            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            // lanes holding the same digit: composed from one ballot per digit bit (cheaper than MATCH.ANY at <= 9 bits)
+            const unsigned vb = __ballot_sync(0xffffffffu, valid);
+            unsigned peers = valid ? vb : ~vb;
+            for (int b = 0; b < p.bits; ++b) {
+                const bool bit = (d >> b) & 1u;
+                const unsigned bal = __ballot_sync(0xffffffffu, bit);
+                peers &= bit ? bal : ~bal;
+            }
             const unsigned before = __popc(peers & lanemask_lt());
             uint32_t old = 0;
             if (valid && before == 0) {   // lowest lane of each digit group bumps the warp-private counter
@@ -331,10 +347,10 @@ struct PassPlan {
 };
 
 static void plan_bits(PassPlan& plan, int total_bits, int key_is_row) {
-    const int passes = (total_bits + 7) / 8;
+    const int passes = (total_bits + SORT_MAX_BITS - 1) / SORT_MAX_BITS;
     int done = 0;
     for (int i = 0; i < passes; ++i) {
-        int b = (total_bits - done + (passes - i) - 1) / (passes - i);   // spread evenly, <= 8
+        int b = (total_bits - done + (passes - i) - 1) / (passes - i);   // spread evenly, <= SORT_MAX_BITS
         plan.key_is_row[plan.n] = key_is_row;
         plan.shift[plan.n] = done;
         plan.bits[plan.n] = b;
