@@ -45,6 +45,9 @@ constexpr int ROUND0_BLOCKS = B200RET_ROUND0_BLOCKS;   // first round / safe-sch
 #ifndef B200RET_SHORT_STEP      // one-row code path for steps whose slice ends inside row 0 (tuning knob)
 #define B200RET_SHORT_STEP 0     // measured SLOWER (138.7 vs 128.7 ms): the warp-uniform branch costs more than the dead slots
 #endif
+#ifndef B200RET_PTX_ADVANCE     // branch-free predicated cursor step in PTX instead of the C++ if/else (tuning knob)
+#define B200RET_PTX_ADVANCE 1
+#endif
 #ifndef B200RET_STEP_ROWS
 #define B200RET_STEP_ROWS 4
 #endif
@@ -154,9 +157,11 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const Sc
             desc[64 + lane] = __float_as_uint(seg_qw);
             __syncwarp();
 
-            // Warp-uniform cursor over 128-byte aligned rows of 32 postings; a step covers up to R rows of ONE slice.
+            // Warp-uniform cursor over 256-byte aligned rows of 32 postings; a step covers up to R rows of ONE slice.
             unsigned c_row = 0, c_beg = 0, c_end = 0;
             float c_qw = 0.f;
+            const uint32_t desc_s = static_cast<uint32_t>(__cvta_generic_to_shared(desc));
+            (void)desc_s;
             // Fetch one step into registers (ids = -1 on dead lanes).  Returns false when nothing is left.
             // Everything is predicated per lane: uniform branches around the rows past a short slice were measured
             // slower (register ring spills, lost overlap) than the dead L1 data-pipe slots they save.
@@ -164,6 +169,41 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const Sc
             // slice begin (wraps to a huge value before the slice), len = slice length (0 = empty step).  The loads leave
             // dead lanes' registers unwritten (no initialisation moves); consume() re-derives the same predicates.
             // advance(): the warp-uniform cursor logic of one step (no memory traffic except 3 LDS at a slice change)
+#if B200RET_PTX_ADVANCE
+            // branch-free cursor step: every state change is predicated on "slice exhausted and another one pending"
+            auto advance = [&](float& qw, unsigned& rel, unsigned& len, const uint2*& row0) -> bool {
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred adv, have, take, dead;\n\t"
+                    ".reg .u32 j, t, a;\n\t"
+                    "setp.ge.u32 adv, %0, %2;\n\t"                  // c_row >= c_end : current slice exhausted
+                    "setp.ne.u32 have, %4, 0;\n\t"
+                    "and.pred take, adv, have;\n\t"
+                    "not.pred have, have;\n\t"
+                    "and.pred dead, adv, have;\n\t"                 // exhausted and nothing pending: empty step
+                    "brev.b32 t, %4;\n\t"
+                    "clz.b32 j, t;\n\t"                             // index of the lowest pending slice
+                    "add.u32 t, %4, -1;\n\t"
+                    "@take and.b32 %4, %4, t;\n\t"
+                    "shl.b32 a, j, 2;\n\t"
+                    "add.u32 a, a, %6;\n\t"
+                    "@take ld.shared.u32 %1, [a];\n\t"              // c_beg
+                    "@take ld.shared.u32 %2, [a + 128];\n\t"        // c_end
+                    "@take ld.shared.f32 %3, [a + 256];\n\t"        // c_qw
+                    "@take and.b32 %0, %1, 0xffffffe0;\n\t"         // c_row = c_beg rounded down to a row
+                    "sub.u32 %5, %2, %1;\n\t"
+                    "@dead mov.u32 %5, 0;\n\t"                      // len
+                    "}\n"
+                    : "+r"(c_row), "+r"(c_beg), "+r"(c_end), "+f"(c_qw), "+r"(pending), "=r"(len)
+                    : "r"(desc_s)
+                    : "memory");
+                qw = c_qw;
+                rel = c_row + lane - c_beg;
+                row0 = g_post + c_row;
+                c_row += 32u * R;
+                return len != 0u;
+            };
+#else
             auto advance = [&](float& qw, unsigned& rel, unsigned& len, const uint2*& row0) -> bool {
                 bool more = true;
                 if (c_row >= c_end) {                      // warp-uniform: current slice exhausted
@@ -185,6 +225,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const Sc
                 c_row += 32u * R;
                 return more;
             };
+#endif
             auto fetch = [&](int (&id)[R], float (&w)[R], float& qw, unsigned& rel, unsigned& len) -> bool {
                 const uint2* row0;
                 const bool more = advance(qw, rel, len, row0);
@@ -346,9 +387,9 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const Sc
             int id[S][R];
             float w[S][R], qw[S];
             unsigned rel[S], len[S];
-            bool more[S];
+            // An empty step (nothing left to fetch) has len == 0; no separate flags are carried through the ring.
 #pragma unroll
-            for (int s = 0; s < S - 1; ++s) more[s] = fetch(id[s], w[s], qw[s], rel[s], len[s]);
+            for (int s = 0; s < S - 1; ++s) fetch(id[s], w[s], qw[s], rel[s], len[s]);
             bool running = true;
             while (running) {
 #pragma unroll
@@ -356,15 +397,15 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const Sc
                     const int f = (s + S - 1) % S;                 // slot freed by the previous consume
 #if B200RET_FUSED_STEP
                     const uint2* frow0;
-                    more[f] = advance(qw[f], rel[f], len[f], frow0);
-                    if (!more[s]) {                                // oldest step is empty: nothing is left at all
+                    advance(qw[f], rel[f], len[f], frow0);
+                    if (len[s] == 0u) {                            // oldest step is empty: nothing is left at all
                         running = false;
                         break;
                     }
                     fused(id[s], w[s], qw[s], rel[s], len[s], id[f], w[f], rel[f], len[f], frow0);
 #else
-                    more[f] = fetch(id[f], w[f], qw[f], rel[f], len[f]);
-                    if (!more[s]) {                                // oldest step is empty: nothing is left at all
+                    fetch(id[f], w[f], qw[f], rel[f], len[f]);
+                    if (len[s] == 0u) {                            // oldest step is empty: nothing is left at all
                         running = false;
                         break;
                     }
