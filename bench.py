@@ -219,18 +219,24 @@ def run_b200(args):
     # in the timed region; the samples it takes during warm-up + timed steps are all under the same load.
     sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(args.warmup):
-        step()
+        out = step()   # held like in the timed loop: the allocator's second set of output blocks is created here, not there
     ops.profile_read(ops.PROF_SPARSE_SCORE)     # drop warm-up records and launch counts
     ops.profile_read(ops.PROF_SPARSE_SELECT)
 
     # ---- device-resident throughput (`value`) ----------------------------------------------------------------
     barrier()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = []
     start.record()
     for _ in range(args.steps):
         out = step()
+        if os.environ.get("B200RET_BENCH_DEBUG"):
+            marks.append(torch.cuda.Event(enable_timing=True))
+            marks[-1].record()
     end.record()
     barrier()
+    if marks:
+        print("per-step ms:", [round(a.elapsed_time(b), 2) for a, b in zip([start] + marks[:-1], marks)], file=sys.stderr)
     clocks = sampler.stop() if sampler else None
     ms_total = torch.tensor([start.elapsed_time(end)], device=dev)
     score_ms, score_launches, all_launches = ops.profile_read(ops.PROF_SPARSE_SCORE)
@@ -374,7 +380,7 @@ def run_b200_dense(args):
     ops.profile_enable(True)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(args.warmup):
-        step()
+        out = step()   # held like in the timed loop (see run_b200)
     ops.profile_read(ops.PROF_DENSE_GEMM)
     ops.profile_read(ops.PROF_SPARSE_SELECT)
     barrier()

@@ -45,6 +45,9 @@ constexpr int ROUND0_BLOCKS = B200RET_ROUND0_BLOCKS;   // first round / safe-sch
 #ifndef B200RET_SKIP_EMPTY      // branch around the accumulate of an empty step (else it runs fully predicated off)
 #define B200RET_SKIP_EMPTY 1
 #endif
+#ifndef B200RET_RING_CHECKS     // control points per revolution of the register ring (1 or 2)
+#define B200RET_RING_CHECKS 1      // 2 measured slower (124.2 vs 119.2 ms per step): the second copy of the control code costs more than the empty steps it saves
+#endif
 #ifndef B200RET_PIPE_DEPTH
 #define B200RET_PIPE_DEPTH 5
 #endif
@@ -399,7 +402,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
     //   * when the cursor has exhausted its term group, the remaining fetches of the revolution return empty steps
     //     (len == 0); at the boundary the next group is installed and the input pipeline moves one stage forward;
     //   * if that group was the item's last, the item's steps were all fetched before this boundary, so they are all
-    //     consumed during the coming revolution: its tile is swept at the NEXT boundary (sweep_due), before the first step
+    //     consumed during the coming revolution: its tile is swept one revolution later (sweep_cd), before the first step
     //     of the following item (fetched during the coming revolution) is consumed.
     constexpr int S = PIPE_DEPTH;
     int id[S][R];
@@ -409,31 +412,34 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
     for (int s = 0; s < S; ++s) len[s] = 0u;
     FetchStages fs(p, ctrl, lane);
     uint32_t acc_rel_s = acc_s - static_cast<uint32_t>(st.a_blk * BD) * 4u;   // tile base of the first item (group a)
-    bool sweep_due = false, fin = false;
+    // Control points: CHECKS per revolution (before body 0 and, with 2, before body S/2 + 1).  Whatever their spacing, the S
+    // steps in the ring at a control point are consumed exactly CHECKS control points later: countdowns in control points.
+    constexpr int CHECKS = B200RET_RING_CHECKS;
+    constexpr int MID = S / 2 + 1;
+    int sweep_cd = 0, fin_cd = 0;
     int sw_q = 0, sw_doc_base = 0;
     float sw_tau = 0.f;
     uint32_t sw_next_acc_rel = 0;
-    while (true) {
-        if (sweep_due) {
+    auto control = [&]() -> bool {      // returns false when the warp is done
+        if (sweep_cd != 0 && --sweep_cd == 0) {
             sweep_tile(p, acc, sw_q, sw_doc_base, sw_tau, lane);
             acc_rel_s = sw_next_acc_rel;
-            sweep_due = false;
         }
-        if (fin) break;
+        if (fin_cd != 0) return --fin_cd != 0;
         while (pending == 0u && c_row >= c_end) {             // group exhausted: warp-uniform, once per term group
             unsigned flags = st.flags;
             if ((flags & (K_VALID | K_LAST | K_MARKED)) == (K_VALID | K_LAST)) {   // the item is complete in the ring: close it
-                if (sweep_due) break;                         // (an item without postings right behind: one sweep per boundary)
+                if (sweep_cd != 0) break;                     // (an item without postings right behind: one sweep at a time)
                 fs.st.flags = flags | K_MARKED;
                 flags |= K_MARKED;
-                sweep_due = true;
+                sweep_cd = CHECKS;
                 sw_q = st.k_q;
                 sw_doc_base = st.k_blk * BD;
-                sw_tau = p.tau ? __ldg(p.tau + sw_q) : 0.f;   // arrives during the coming revolution
+                sw_tau = p.tau ? __ldg(p.tau + sw_q) : 0.f;   // arrives while the item's last steps are consumed
                 sw_next_acc_rel = acc_s - static_cast<uint32_t>(((flags & A_VALID) ? st.a_blk : st.k_blk) * BD) * 4u;
             }
             if (!(flags & A_VALID)) {
-                fin = true;
+                fin_cd = CHECKS;
                 break;
             }
             // install group a (its skip-table entries were requested one group ago), then move the stages forward
@@ -453,8 +459,18 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
             fs.st.flags = flags;
             if (fs.want_claim && lane == 0) nn_item = atomicAdd(p.item_counter, 1u);   // stays in flight
         }
+        return true;
+    };
+    bool running = true;
+    while (running) {
 #pragma unroll
         for (int s = 0; s < S; ++s) {
+            if (s == 0 || (CHECKS == 2 && s == MID)) {
+                if (!control()) {
+                    running = false;
+                    break;
+                }
+            }
 #if B200RET_SKIP_EMPTY
             if (len[s] != 0u)
 #endif
