@@ -48,6 +48,9 @@ constexpr int ROUND0_BLOCKS = B200RET_ROUND0_BLOCKS;   // first round / safe-sch
 #ifndef B200RET_RING_CHECKS     // control points per revolution of the register ring (1 or 2)
 #define B200RET_RING_CHECKS 1      // 2 measured slower (124.2 vs 119.2 ms per step): the second copy of the control code costs more than the empty steps it saves
 #endif
+#ifndef B200RET_BATCH_STEPS     // > 0: two double-buffered register batches of this many steps instead of the ring
+#define B200RET_BATCH_STEPS 3
+#endif
 #ifndef B200RET_PIPE_DEPTH
 #define B200RET_PIPE_DEPTH 5
 #endif
@@ -330,17 +333,22 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
     };
     // Fetch one step into ring registers.  The cold path (once per term group) installs the next group's descriptors,
     // moves the input pipeline one stage forward, or emits a control record (end of item / no work left).
-    auto fetch = [&](int (&id)[R], float (&w)[R], float& qw, unsigned& rel, unsigned& len) {
+    // `dep` is a doc id loaded by the batch that is about to be accumulated (always < 2^31): the loads are made to depend on
+    // it (dep >> 31 == 0 is added to the lane position), so they cannot be issued before that batch's loads have landed —
+    // see the main loop for why this order matters.
+    auto fetch = [&](int (&id)[R], float (&w)[R], float& qw, unsigned& rel, unsigned& len, int dep) {
         const uint2* row0;
         advance(qw, rel, len, row0);
         asm volatile(
             "{\n\t"
             ".reg .pred p0, p1, p2, p3;\n\t"
-            ".reg .u32 t1, t2, t3;\n\t"
-            "add.u32 t1, %8, 32;\n\t"
-            "add.u32 t2, %8, 64;\n\t"
-            "add.u32 t3, %8, 96;\n\t"
-            "setp.lt.u32 p0, %8, %9;\n\t"
+            ".reg .u32 t0, t1, t2, t3;\n\t"
+            "shr.u32 t0, %11, 31;\n\t"
+            "add.u32 t0, t0, %8;\n\t"
+            "add.u32 t1, t0, 32;\n\t"
+            "add.u32 t2, t0, 64;\n\t"
+            "add.u32 t3, t0, 96;\n\t"
+            "setp.lt.u32 p0, t0, %9;\n\t"
             "setp.lt.u32 p1, t1, %9;\n\t"
             "setp.lt.u32 p2, t2, %9;\n\t"
             "setp.lt.u32 p3, t3, %9;\n\t"
@@ -349,8 +357,8 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
             "@p2 " B200RET_LDNC ".v2.b32 {%2, %6}, [%10 + 512];\n\t"
             "@p3 " B200RET_LDNC ".v2.b32 {%3, %7}, [%10 + 768];\n\t"
             "}\n"
-            : "=r"(id[0]), "=r"(id[1]), "=r"(id[2]), "=r"(id[3]), "=f"(w[0]), "=f"(w[1]), "=f"(w[2]), "=f"(w[3])
-            : "r"(rel), "r"(len), "l"(row0));
+            : "+r"(id[0]), "+r"(id[1]), "+r"(id[2]), "+r"(id[3]), "+f"(w[0]), "+f"(w[1]), "+f"(w[2]), "+f"(w[3])
+            : "r"(rel), "r"(len), "l"(row0), "r"(dep));
     };
     // Accumulate one step.  Its rows belong to ONE posting list, so their doc ids are distinct and the R
     // read-modify-writes are independent: loads, adds and stores are issued R-wide (one latency per step).
@@ -395,7 +403,138 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
             : "memory");
         __syncwarp();   // orders this step's shared-memory updates before the next step (possibly the next term)
     };
+    // The same accumulate in two parts: the score-slot addresses (first use of the loaded doc ids: the scoreboard wait for
+    // the batch's loads happens here), and the read-modify-writes.
+    auto consume_pre = [&](const int (&id)[R], uint32_t (&d)[R], uint32_t acc_rel_s) {
+        asm volatile(
+            "mad.lo.u32 %0, %4, 4, %8;\n\t"
+            "mad.lo.u32 %1, %5, 4, %8;\n\t"
+            "mad.lo.u32 %2, %6, 4, %8;\n\t"
+            "mad.lo.u32 %3, %7, 4, %8;\n"
+            : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+            : "r"(id[0]), "r"(id[1]), "r"(id[2]), "r"(id[3]), "r"(acc_rel_s));
+    };
+    auto consume_rest = [&](const uint32_t (&d)[R], const float (&w)[R], float qw, unsigned rel, unsigned len) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p0, p1, p2, p3;\n\t"
+            ".reg .f32 a0, a1, a2, a3, v0, v1, v2, v3;\n\t"
+            ".reg .u32 t1, t2, t3;\n\t"
+            "add.u32 t1, %9, 32;\n\t"
+            "add.u32 t2, %9, 64;\n\t"
+            "add.u32 t3, %9, 96;\n\t"
+            "setp.lt.u32 p0, %9, %10;\n\t"
+            "setp.lt.u32 p1, t1, %10;\n\t"
+            "setp.lt.u32 p2, t2, %10;\n\t"
+            "setp.lt.u32 p3, t3, %10;\n\t"
+            "@p0 ld.shared.f32 a0, [%0];\n\t"
+            "@p1 ld.shared.f32 a1, [%1];\n\t"
+            "@p2 ld.shared.f32 a2, [%2];\n\t"
+            "@p3 ld.shared.f32 a3, [%3];\n\t"
+            "mul.rn.f32 v0, %8, %4;\n\t"
+            "mul.rn.f32 v1, %8, %5;\n\t"
+            "mul.rn.f32 v2, %8, %6;\n\t"
+            "mul.rn.f32 v3, %8, %7;\n\t"
+            "@p0 add.rn.f32 a0, a0, v0;\n\t"
+            "@p1 add.rn.f32 a1, a1, v1;\n\t"
+            "@p2 add.rn.f32 a2, a2, v2;\n\t"
+            "@p3 add.rn.f32 a3, a3, v3;\n\t"
+            "@p0 st.shared.f32 [%0], a0;\n\t"
+            "@p1 st.shared.f32 [%1], a1;\n\t"
+            "@p2 st.shared.f32 [%2], a2;\n\t"
+            "@p3 st.shared.f32 [%3], a3;\n\t"
+            "}\n" ::"r"(d[0]), "r"(d[1]), "r"(d[2]), "r"(d[3]), "f"(w[0]), "f"(w[1]), "f"(w[2]), "f"(w[3]), "f"(qw), "r"(rel), "r"(len)
+            : "memory");
+        __syncwarp();
+    };
+    (void)consume;
+    (void)consume_pre;
+    (void)consume_rest;
 
+#if B200RET_BATCH_STEPS > 0
+    // Two register batches of HB steps each, double-buffered: all posting loads of a warp share ONE hardware scoreboard
+    // (ptxas gives the other five to the shared-memory loads), so "wait for this step's loads" means "wait for every load in
+    // flight".  A ring that fetches one step per consumed step therefore exposes the full load latency again and again (ptxas
+    // answers by sinking all loads to the end of the revolution: no overlap at all).  Here the order is
+    //     wait(A) -> issue loads of B -> accumulate A -> wait(B) -> issue loads of A -> accumulate B -> ...
+    // so every wait finds only loads that have been in flight for a whole batch's accumulate time.
+    // Control (one copy of the cold code): group install / item close at the top (before the loads of B are issued), the
+    // sweep of a closed item between the two halves: the item's last steps are in A, the next item's first steps in B.
+    constexpr int HB = B200RET_BATCH_STEPS;
+    int id[2 * HB][R];
+    float w[2 * HB][R], qw[2 * HB];
+    unsigned rel[2 * HB], len[2 * HB];
+#pragma unroll
+    for (int s = 0; s < 2 * HB; ++s) {
+        len[s] = 0u;
+        qw[s] = 0.f;
+        rel[s] = 0u;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {     // dead lanes keep old register contents: make sure they are always doc ids (< 2^31)
+            id[s][r] = 0;
+            w[s][r] = 0.f;
+        }
+    }
+    FetchStages fs(p, ctrl, lane);
+    uint32_t acc_rel_s = acc_s - static_cast<uint32_t>(st.a_blk * BD) * 4u;   // tile base of the first item (group a)
+    bool sweep_due = false, fin = false;
+    int sw_q = 0, sw_doc_base = 0;
+    float sw_tau = 0.f;
+    uint32_t sw_next_acc_rel = 0;
+    auto half = [&](int c0, int f0) {     // accumulate batch [c0, c0 + HB) while the loads of batch [f0, f0 + HB) are issued
+        uint32_t d[HB][R];
+#pragma unroll
+        for (int s = 0; s < HB; ++s) consume_pre(id[c0 + s], d[s], acc_rel_s);
+#pragma unroll
+        for (int s = 0; s < HB; ++s) fetch(id[f0 + s], w[f0 + s], qw[f0 + s], rel[f0 + s], len[f0 + s], id[c0][0]);
+#pragma unroll
+        for (int s = 0; s < HB; ++s)
+            if (len[c0 + s] != 0u) consume_rest(d[s], w[c0 + s], qw[c0 + s], rel[c0 + s], len[c0 + s]);
+    };
+    while (!fin) {
+        while (pending == 0u && c_row >= c_end) {             // group exhausted: warp-uniform, once per term group
+            unsigned flags = st.flags;
+            if ((flags & (K_VALID | K_LAST | K_MARKED)) == (K_VALID | K_LAST)) {   // the item is complete (its last steps are in A)
+                if (sweep_due) break;                         // (an item without postings right behind: one sweep per iteration)
+                fs.st.flags = flags | K_MARKED;
+                flags |= K_MARKED;
+                sweep_due = true;
+                sw_q = st.k_q;
+                sw_doc_base = st.k_blk * BD;
+                sw_tau = p.tau ? __ldg(p.tau + sw_q) : 0.f;   // arrives while A is accumulated
+                sw_next_acc_rel = acc_s - static_cast<uint32_t>(((flags & A_VALID) ? st.a_blk : st.k_blk) * BD) * 4u;
+            }
+            if (!(flags & A_VALID)) {
+                fin = true;                                   // A is still accumulated (and swept) in this iteration
+                break;
+            }
+            // install group a (its skip-table entries were requested one group ago), then move the stages forward
+            cp_async_wait_all();
+            __syncwarp();
+            const unsigned gen = st.gen;
+            const uint32_t* buf = ctrl + CTRL_DESC + (gen & 1u) * 96;
+            pending = __ballot_sync(FULL, buf[32 + lane] > buf[lane]);   // non-empty slices, ascending term order
+            desc_s = desc_s01 - desc_s;                       // the cursor reads slice j's descriptor with 3 broadcast LDS.32
+            fs.st.k_q = st.a_q;
+            fs.st.k_blk = st.a_blk;
+            flags = (flags & ~(K_VALID | K_LAST | K_MARKED)) | K_VALID | ((flags & A_LAST) ? K_LAST : 0u);
+            fs.want_claim = false;
+            fs.stage_table(flags, ctrl + CTRL_DESC + ((gen + 1u) & 1u) * 96);
+            fs.stage_terms(flags, __shfl_sync(FULL, nn_item, 0));
+            fs.st.gen = gen + 1u;
+            fs.st.flags = flags;
+            if (fs.want_claim && lane == 0) nn_item = atomicAdd(p.item_counter, 1u);   // stays in flight
+        }
+        half(0, HB);
+        if (sweep_due) {
+            sweep_tile(p, acc, sw_q, sw_doc_base, sw_tau, lane);
+            acc_rel_s = sw_next_acc_rel;
+            sweep_due = false;
+        }
+        half(HB, 0);
+    }
+}
+#else
     // S steps in flight in a register ring: consume step i, then fetch step i+S into the freed slot.  The ring indices are
     // compile-time constants after unrolling, so the slots stay in registers.  All control work happens at the boundary
     // between two revolutions of the ring (one copy of the cold code, no calls, nothing in the hot loop but the steps):
@@ -475,10 +614,11 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
             if (len[s] != 0u)
 #endif
                 consume(id[s], w[s], qw[s], rel[s], len[s], acc_rel_s);
-            fetch(id[s], w[s], qw[s], rel[s], len[s]);
+            fetch(id[s], w[s], qw[s], rel[s], len[s], 0);
         }
     }
 }
+#endif
 
 static int block_docs_of_shape() { return BLOCK_DOCS; }
 
