@@ -14,15 +14,21 @@
 
 namespace b200ret {
 
-constexpr int SORT_THREADS = 512;
+constexpr int SORT_THREADS = 1024;                             // one CTA per SM
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_ROUNDS = 8;                                  // postings per lane per tile
-constexpr int SORT_TILE = SORT_THREADS * SORT_ROUNDS;           // 4096 postings per tile
+constexpr int SORT_TILE = SORT_THREADS * SORT_ROUNDS;           // 8192 postings per tile
 #ifndef B200RET_SORT_BITS
 #define B200RET_SORT_BITS 9       // digit width per pass: 17-bit term ids sort in 2 passes (9 + 8)
 #endif
 constexpr int SORT_MAX_BITS = B200RET_SORT_BITS;
 constexpr int SORT_MAX_BUCKETS = 1 << SORT_MAX_BITS;
+// scatter kernel shared memory: per-warp digit counters (16 bit: a warp holds 256 postings of a tile), digit tables, and the
+// tile staged in digit order (row, col, val) so that the global writes are contiguous runs per digit
+constexpr size_t SORT_SCATTER_SMEM = static_cast<size_t>(SORT_WARPS) * SORT_MAX_BUCKETS * sizeof(uint16_t) +
+                                     3 * SORT_MAX_BUCKETS * sizeof(uint32_t) + 64 * sizeof(uint32_t) +
+                                     3 * static_cast<size_t>(SORT_TILE) * sizeof(uint32_t);
+static_assert(SORT_SCATTER_SMEM <= 227 * 1024, "scatter tile exceeds shared memory");
 
 struct SortPass {
     const int32_t* src_row;
@@ -92,10 +98,26 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(uint32_t* __restrict__ 
     }
 }
 
-__global__ void __launch_bounds__(SORT_THREADS, 2) sort_scatter_kernel(SortPass p, int64_t nnz, int64_t per_block,
+// One pass of the stable LSD sort.  Per tile of 8192 postings (feed order = warp-major, round-major, lane-minor):
+//   1. rank every posting among the postings of the same digit in its warp (ballot multisplit, warp-private counters);
+//   2. scan the counters over warps and digits -> position of every posting in the tile's digit-sorted order;
+//   3. stage the tile in that order in shared memory;
+//   4. copy it out: consecutive threads hold consecutive postings of a digit, whose destinations are consecutive too
+//      (global base of the digit + offset inside the tile's run), so the stores are contiguous runs of ~16-32 postings
+//      instead of one 4-byte scattered store per posting and array (the previous version of this kernel was bound by L2
+//      store transactions: 350 GB/s).
+__global__ void __launch_bounds__(SORT_THREADS, 1) sort_scatter_kernel(SortPass p, int64_t nnz, int64_t per_block,
                                                                     const uint32_t* __restrict__ bases) {
-    __shared__ uint32_t wcnt[SORT_WARPS][SORT_MAX_BUCKETS];
-    __shared__ uint32_t gbase[SORT_MAX_BUCKETS];
+    extern __shared__ __align__(16) unsigned char sort_smem[];
+    uint16_t* const wcnt = reinterpret_cast<uint16_t*>(sort_smem);                                   // [SORT_WARPS][buckets]
+    uint32_t* const gbase = reinterpret_cast<uint32_t*>(wcnt + SORT_WARPS * SORT_MAX_BUCKETS);       // running global offset per digit
+    uint32_t* const tbase = gbase + SORT_MAX_BUCKETS;                                                // start of the digit's run inside the tile
+    uint32_t* const ttot = tbase + SORT_MAX_BUCKETS;                                                 // postings of the digit in the tile
+    uint32_t* const wsum = ttot + SORT_MAX_BUCKETS;                                                  // [32] scan scratch
+    int32_t* const s_row = reinterpret_cast<int32_t*>(wsum + 64);
+    int32_t* const s_col = s_row + SORT_TILE;
+    float* const s_val = reinterpret_cast<float*>(s_col + SORT_TILE);
+
     const int buckets = 1 << p.bits;
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
@@ -104,12 +126,13 @@ __global__ void __launch_bounds__(SORT_THREADS, 2) sort_scatter_kernel(SortPass 
     const int64_t lo = static_cast<int64_t>(blockIdx.x) * per_block;
     const int64_t hi = min(nnz, lo + per_block);
     for (int64_t tile = lo; tile < hi; tile += SORT_TILE) {
-        for (int i = threadIdx.x; i < SORT_WARPS * buckets; i += SORT_THREADS) wcnt[i / buckets][i % buckets] = 0;
+        for (int i = threadIdx.x; i < SORT_WARPS * buckets / 2; i += SORT_THREADS) reinterpret_cast<uint32_t*>(wcnt)[i] = 0;
         __syncthreads();
 
         int32_t row[SORT_ROUNDS], col[SORT_ROUNDS];
         float val[SORT_ROUNDS];
-        uint32_t rank[SORT_ROUNDS], dig[SORT_ROUNDS];
+        uint32_t rank[SORT_ROUNDS];
+        uint16_t* const my_cnt = wcnt + warp * buckets;
         // Warp w owns the contiguous slice [tile + w*256, +256): round-major, lane-minor == feed order.
         const int64_t wbase = tile + static_cast<int64_t>(warp) * (32 * SORT_ROUNDS);
 #pragma unroll
@@ -123,8 +146,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 2) sort_scatter_kernel(SortPass 
 #pragma unroll
         for (int r = 0; r < SORT_ROUNDS; ++r) {
             const bool valid = (wbase + r * 32 + lane) < hi;
-            const uint32_t d = valid ? pass_digit(p, row[r], col[r]) : 0xffffffffu;
-            dig[r] = d;
+            const uint32_t d = pass_digit(p, row[r], col[r]);
             // lanes holding the same digit: composed from one ballot per digit bit (cheaper than MATCH.ANY at <= 9 bits)
             const unsigned vb = __ballot_sync(0xffffffffu, valid);
             unsigned peers = valid ? vb : ~vb;
@@ -136,36 +158,78 @@ __global__ void __launch_bounds__(SORT_THREADS, 2) sort_scatter_kernel(SortPass 
             const unsigned before = __popc(peers & lanemask_lt());
             uint32_t old = 0;
             if (valid && before == 0) {   // lowest lane of each digit group bumps the warp-private counter
-                old = wcnt[warp][d];
-                wcnt[warp][d] = old + __popc(peers);
+                old = my_cnt[d];
+                my_cnt[d] = static_cast<uint16_t>(old + __popc(peers));
             }
             old = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1);
             rank[r] = old + before;
             __syncwarp();
         }
         __syncthreads();
-        // Per digit: exclusive scan over warps, rebased on the block's running global offset.
-        for (int d = threadIdx.x; d < buckets; d += SORT_THREADS) {
-            uint32_t run = gbase[d];
-#pragma unroll
+        // Per digit: exclusive scan of the counters over warps; total of the digit in the tile.
+        uint32_t my_tot = 0;
+        if (threadIdx.x < buckets) {
+            const int d = threadIdx.x;
+            uint32_t run = 0;
+#pragma unroll 8
             for (int w = 0; w < SORT_WARPS; ++w) {
-                uint32_t c = wcnt[w][d];
-                wcnt[w][d] = run;
+                const uint32_t c = wcnt[w * buckets + d];
+                wcnt[w * buckets + d] = static_cast<uint16_t>(run);
                 run += c;
             }
-            gbase[d] = run;
+            my_tot = run;
+            ttot[d] = run;
+        }
+        // Exclusive scan of the totals over digits -> start of every digit's run in the staged tile.
+        {
+            uint32_t incl = my_tot;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += v;
+            }
+            if (lane == 31) wsum[warp] = incl;
+            __syncthreads();
+            if (warp == 0) {
+                uint32_t t = wsum[lane];
+                uint32_t ti = t;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, ti, off);
+                    if (lane >= off) ti += v;
+                }
+                wsum[32 + lane] = ti - t;
+            }
+            __syncthreads();
+            if (threadIdx.x < buckets) tbase[threadIdx.x] = wsum[32 + warp] + incl - my_tot;
         }
         __syncthreads();
 #pragma unroll
         for (int r = 0; r < SORT_ROUNDS; ++r) {
-            if (dig[r] != 0xffffffffu) {
-                const uint32_t pos = wcnt[warp][dig[r]] + rank[r];
-                p.dst_row[pos] = row[r];
-                p.dst_col[pos] = col[r];
-                p.dst_val[pos] = val[r];
+            if ((wbase + r * 32 + lane) < hi) {
+                const uint32_t d = pass_digit(p, row[r], col[r]);
+                const uint32_t li = tbase[d] + my_cnt[d] + rank[r];
+                s_row[li] = row[r];
+                s_col[li] = col[r];
+                s_val[li] = val[r];
             }
         }
         __syncthreads();
+        const int n_tile = static_cast<int>(min(static_cast<int64_t>(SORT_TILE), hi - tile));
+#pragma unroll
+        for (int r = 0; r < SORT_ROUNDS; ++r) {
+            const int j = r * SORT_THREADS + threadIdx.x;
+            if (j < n_tile) {
+                const int32_t rw = s_row[j], cl = s_col[j];
+                const uint32_t d = pass_digit(p, rw, cl);
+                const uint32_t pos = gbase[d] + (static_cast<uint32_t>(j) - tbase[d]);
+                p.dst_row[pos] = rw;
+                p.dst_col[pos] = cl;
+                p.dst_val[pos] = s_val[j];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < buckets) gbase[threadIdx.x] += my_tot;
     }
 }
 
@@ -366,7 +430,7 @@ static PassPlan make_plan(int32_t n_terms, int32_t n_docs, int sort_docs) {
     return plan;
 }
 
-static int sort_grid() { return sm_count() * 2; }
+static int sort_grid() { return sm_count(); }
 
 }  // namespace b200ret
 
@@ -416,6 +480,12 @@ extern "C" int b200ret_csr_build(const int32_t* rows, const int32_t* cols, const
     int64_t per_block = (nnz + grid - 1) / grid;
     per_block = (per_block + SORT_TILE - 1) / SORT_TILE * SORT_TILE;
 
+    static bool attr_set = false;
+    if (!attr_set) {
+        B200RET_CUDA_CHECK(cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                static_cast<int>(SORT_SCATTER_SMEM)));
+        attr_set = true;
+    }
     const PassPlan plan = make_plan(n_terms, n_docs, sort_docs);
     const int32_t* src_row = rows;
     const int32_t* src_col = cols;
@@ -434,7 +504,7 @@ extern "C" int b200ret_csr_build(const int32_t* rows, const int32_t* cols, const
         prof_begin(PROF_CSR_SORT, stream);
         sort_hist_kernel<<<grid, SORT_THREADS, 0, stream>>>(p, nnz, per_block, counts);
         sort_scan_kernel<<<1, 1024, 0, stream>>>(counts, buckets * grid);
-        sort_scatter_kernel<<<grid, SORT_THREADS, 0, stream>>>(p, nnz, per_block, counts);
+        sort_scatter_kernel<<<grid, SORT_THREADS, SORT_SCATTER_SMEM, stream>>>(p, nnz, per_block, counts);
         prof_end(PROF_CSR_SORT, stream);
         count_launches(3);
         B200RET_CUDA_CHECK(cudaGetLastError());

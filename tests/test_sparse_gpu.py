@@ -231,6 +231,35 @@ def test_search_long_query_and_negative_threshold(cuda):
         assert np.array_equal(scores.cpu().numpy().view(np.uint32), o_scores.view(np.uint32))
 
 
+def test_search_ragged_query_mix_exercises_pipeline_control(cuda):
+    """Runs of empty queries, one-term queries and 150-term queries (five term groups) over a corpus whose postings sit in a
+    few doc blocks only: items without any posting directly behind each other, groups with only empty slices, warps that
+    get no item at all — every control path of the score kernel's never-draining load pipeline, vs the C oracle."""
+    n_docs, n_terms = 3328 * 9 + 17, 600
+    g = torch.Generator(device="cpu").manual_seed(77)
+    rows, cols, vals = synth.gen_sparse_docs(n_docs, n_terms=n_terms, mean_nnz=30, seed=21, device=cuda)
+    keep = ((rows // 3328) % 3 != 1) | (cols % 7 == 0)           # thin out every third doc block
+    rows, cols, vals = rows[keep], cols[keep], vals[keep]
+    index = ops.SparseDeviceIndex.from_coo(rows, cols, vals, n_terms, n_docs)
+    lens = [0, 0, 0, 1, 150, 0, 1, 1, 0, 40, 0, 0, 97, 33, 32, 0, 64, 65, 0, 0, 2, 150, 0]
+    q_terms, q_off = [], [0]
+    for n in lens:
+        t = torch.randperm(n_terms, generator=g)[:n].sort().values
+        q_terms.append(t)
+        q_off.append(q_off[-1] + n)
+    q_t = torch.cat(q_terms).to(torch.int32).to(cuda)
+    q_w = (torch.rand(q_t.numel(), generator=g) + 0.1).to(torch.float32).to(cuda)
+    q_off = torch.tensor(q_off, dtype=torch.int32, device=cuda)
+    for thr, k in [(0.0, 64), (-0.5, 1000)]:
+        scores, ids, counts = ops.sparse_search(index, q_off, q_t, q_w, k, thr)
+        o_scores, o_ids, o_counts = c_oracle.sparse_search(index.term_offsets.cpu().numpy(), index.doc_ids.cpu().numpy(),
+                                                           index.weights.cpu().numpy(), n_docs, q_off.cpu().numpy(),
+                                                           q_t.cpu().numpy(), q_w.cpu().numpy(), k, thr)
+        assert np.array_equal(counts.cpu().numpy(), o_counts)
+        assert np.array_equal(ids.cpu().numpy(), o_ids)
+        assert np.array_equal(scores.cpu().numpy().view(np.uint32), o_scores.view(np.uint32))
+
+
 def test_search_overflow_falls_back_to_safe_schedule(cuda):
     """Adversarial doc order: scores increase with the row id, so every later doc beats the running k-th score and
     the candidate lists overflow in the doubling rounds; the safe re-run must still return the exact top-k."""
