@@ -311,7 +311,8 @@ __global__ void block_table_empty_kernel(const int64_t* __restrict__ term_offset
 // [0, len) - its quantile position in the slice; keys of one bank are >= len/c >= 1 apart, so a key value holds at most one
 // posting per bank.  A counting sort over the key values (shared-memory histogram + warp scan) then yields the permutation:
 // one integer division per posting instead of a comparison sort.
-constexpr int BANK_MAX_WARPS = 4;
+constexpr int BANK_MAX_WARPS = 32;
+constexpr int BANK_SMALL_CAP = 256;     // slices up to this length are laid out by the many-warp launch
 constexpr int BANK_MAX_BLOCK_DOCS = 8192;
 // per-warp shared memory for slices of up to `cap` postings: ids, weights, (key, slot), key counters + 32 bank counters
 static inline size_t bank_warp_smem(int cap) { return static_cast<size_t>(cap) * 16 + 128; }
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(BANK_MAX_WARPS * 32) posting_layout_kernel(con
                                                                               const int32_t* __restrict__ doc_ids,
                                                                               const float* __restrict__ weights, uint2* __restrict__ out,
                                                                               int32_t n_terms, int32_t n_blocks, int32_t cap,
-                                                                              int32_t bank_order) {
+                                                                              int32_t bank_order, int32_t min_len, int32_t max_len) {
     extern __shared__ __align__(16) unsigned char bank_smem[];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
@@ -345,7 +346,8 @@ __global__ void __launch_bounds__(BANK_MAX_WARPS * 32) posting_layout_kernel(con
             beg = table[static_cast<size_t>(t) * row_len + b];
             end = table[static_cast<size_t>(t) * row_len + b + 1];
         }
-        unsigned todo = __ballot_sync(0xffffffffu, end > beg);
+        // this launch handles the slices with min_len < length <= max_len (the shared memory per warp is sized for max_len)
+        unsigned todo = __ballot_sync(0xffffffffu, end - beg > static_cast<uint32_t>(min_len) && end - beg <= static_cast<uint32_t>(max_len));
         while (todo) {
             const int j = __ffs(todo) - 1;
             todo &= todo - 1;
@@ -557,16 +559,23 @@ extern "C" int b200ret_sparse_layout(const uint32_t* table, const int32_t* doc_i
     if (n_blocks == 0 || nnz == 0) return B200RET_OK;
     B200RET_REQUIRE(doc_ids && weights && postings_out, "sparse_layout: null pointer");
     B200RET_REQUIRE(reinterpret_cast<uintptr_t>(postings_out) % 8 == 0, "sparse_layout: postings_out must be 8-byte aligned");
-    const int warps = max(1, min(BANK_MAX_WARPS, static_cast<int>((220 * 1024) / bank_warp_smem(block_docs))));
-    const size_t smem = static_cast<size_t>(warps) * bank_warp_smem(block_docs);
     static bool attr_set = false;
     if (!attr_set) {
         B200RET_CUDA_CHECK(cudaFuncSetAttribute(posting_layout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         attr_set = true;
     }
-    posting_layout_kernel<<<sm_count(), warps * 32, smem, stream>>>(table, doc_ids, weights, static_cast<uint2*>(postings_out),
-                                                                   n_terms, n_blocks, block_docs, bank_order);
-    count_launches(1);
+    // Two launches: the shared memory of a warp is sized for the longest slice it may meet, and almost all slices are
+    // short — sizing every warp for block_docs postings left 4 warps per SM and made the layout latency-bound (0.3 s).
+    const int caps[2] = {min(BANK_SMALL_CAP, block_docs), block_docs};
+    const int mins[2] = {0, caps[0]};
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1 && caps[1] <= caps[0]) break;
+        const int warps = max(1, min(BANK_MAX_WARPS, static_cast<int>((220 * 1024) / bank_warp_smem(caps[pass]))));
+        const size_t smem = static_cast<size_t>(warps) * bank_warp_smem(caps[pass]);
+        posting_layout_kernel<<<sm_count(), warps * 32, smem, stream>>>(table, doc_ids, weights, static_cast<uint2*>(postings_out),
+                                                                       n_terms, n_blocks, caps[pass], bank_order, mins[pass], caps[pass]);
+        count_launches(1);
+    }
     B200RET_CUDA_CHECK(cudaGetLastError());
     return B200RET_OK;
 }
