@@ -39,9 +39,6 @@ constexpr int ROUND0_BLOCKS = B200RET_ROUND0_BLOCKS;   // first round / safe-sch
 #ifndef B200RET_LDNC           // posting-load flavour (tuning knob)
 #define B200RET_LDNC "ld.global.nc"
 #endif
-#ifndef B200RET_SWEEP_EXCH      // sweep with one 64-bit shared atomic exchange (read + zero) instead of LDS.128 + STS.128
-#define B200RET_SWEEP_EXCH 0
-#endif
 #ifndef B200RET_SKIP_EMPTY      // branch around the accumulate of an empty step (else it runs fully predicated off)
 #define B200RET_SKIP_EMPTY 1
 #endif
@@ -49,7 +46,7 @@ constexpr int ROUND0_BLOCKS = B200RET_ROUND0_BLOCKS;   // first round / safe-sch
 #define B200RET_RING_CHECKS 1      // 2 measured slower (124.2 vs 119.2 ms per step): the second copy of the control code costs more than the empty steps it saves
 #endif
 #ifndef B200RET_BATCH_STEPS     // > 0: two double-buffered register batches of this many steps instead of the ring
-#define B200RET_BATCH_STEPS 3
+#define B200RET_BATCH_STEPS 2
 #endif
 #ifndef B200RET_PIPE_DEPTH
 #define B200RET_PIPE_DEPTH 5
@@ -111,36 +108,55 @@ __device__ __forceinline__ void sweep_tile(const ScoreParams& p, float* acc, int
             *reinterpret_cast<float4*>(acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     } else {
+        // Two phases, ONE counter update per item (its round trip blocks the warp; with one update per 128-doc chunk the warps
+        // spent about as long blocked on them as accumulating when the shard is small or tau still low):
+        //   1. read the tile, write it back with everything but the hits zeroed, remember the hits in a per-lane bit mask
+        //      (4 bits per 128-doc chunk);
+        //   2. reserve all slots of the item at once; every lane then emits (and zeroes) its own hits.
         const int limit = min(BD, p.n_docs - doc_base);
         uint64_t* cq = p.cand + static_cast<size_t>(q) * p.cap;
-#if B200RET_SWEEP_EXCH
-        // read-and-zero in one shared-memory instruction (64-bit atomic exchange)
-        for (int i = lane * 2; i < BD; i += 64) {
-            const unsigned long long old = atomicExch(reinterpret_cast<unsigned long long*>(acc + i), 0ULL);
-            const float vc[2] = {__uint_as_float(static_cast<unsigned>(old)), __uint_as_float(static_cast<unsigned>(old >> 32))};
-            const float m = fmaxf(vc[0], vc[1]);
-            if (__any_sync(FULL, (m > tq) && (i < limit))) {
+        constexpr int CHUNKS = BD / 128;
+        unsigned mask[(CHUNKS + 7) / 8];
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-#else
-        for (int i = lane * 4; i < BD; i += 128) {
-            const float4 v = *reinterpret_cast<const float4*>(acc + i);
-            *reinterpret_cast<float4*>(acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float m = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
-            if (__any_sync(FULL, (m > tq) && (i < limit))) {
-                const float vc[4] = {v.x, v.y, v.z, v.w};
+        for (int wd = 0; wd < (CHUNKS + 7) / 8; ++wd) mask[wd] = 0u;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-#endif
-                    const bool hit = (vc[c] > tq) && (i + c < limit);
-                    const unsigned b = __ballot_sync(FULL, hit);
-                    if (b) {
-                        int base = 0;
-                        if (lane == 0) base = atomicAdd(p.cand_count + q, __popc(b));
-                        base = __shfl_sync(FULL, base, 0);
-                        const int pos = base + __popc(b & lanemask_lt());
-                        if (hit && pos < p.cap) cq[pos] = cand_key(vc[c], doc_base + i + c);
-                    }
+        for (int ch = 0; ch < CHUNKS; ++ch) {
+            const int i = ch * 128 + lane * 4;
+            float4 v = *reinterpret_cast<const float4*>(acc + i);
+            const unsigned h = ((v.x > tq) && (i < limit) ? 1u : 0u) | ((v.y > tq) && (i + 1 < limit) ? 2u : 0u) |
+                               ((v.z > tq) && (i + 2 < limit) ? 4u : 0u) | ((v.w > tq) && (i + 3 < limit) ? 8u : 0u);
+            if (!(h & 1u)) v.x = 0.f;
+            if (!(h & 2u)) v.y = 0.f;
+            if (!(h & 4u)) v.z = 0.f;
+            if (!(h & 8u)) v.w = 0.f;
+            *reinterpret_cast<float4*>(acc + i) = v;
+            mask[ch >> 3] |= h << ((ch & 7) * 4);
+        }
+        int mine = 0;
+#pragma unroll
+        for (int wd = 0; wd < (CHUNKS + 7) / 8; ++wd) mine += __popc(mask[wd]);
+        int incl = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int u = __shfl_up_sync(FULL, incl, off);
+            if (lane >= static_cast<unsigned>(off)) incl += u;
+        }
+        const int total = __shfl_sync(FULL, incl, 31);
+        if (total > 0) {                                     // warp-uniform
+            int base = 0;
+            if (lane == 0) base = atomicAdd(p.cand_count + q, total);
+            int pos = __shfl_sync(FULL, base, 0) + incl - mine;
+#pragma unroll
+            for (int wd = 0; wd < (CHUNKS + 7) / 8; ++wd) {
+                unsigned m = mask[wd];
+                while (m) {
+                    const int bit = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int idx = (wd * 8 + (bit >> 2)) * 128 + lane * 4 + (bit & 3);
+                    const float val = acc[idx];
+                    acc[idx] = 0.f;
+                    if (pos < p.cap) cq[pos] = cand_key(val, doc_base + idx);
+                    ++pos;
                 }
             }
         }
