@@ -11,45 +11,65 @@
 namespace b200ret {
 
 constexpr int MERGE_THREADS = 512;
-constexpr int MERGE_MAX_CANDIDATES = 16384;   // 128 KB of keys in shared memory
+constexpr int MERGE_MAX_CANDIDATES = 16384;   // 128 KB of keys in shared memory (+ up to 32 KB of winners)
 
+// One CTA per query: gather the G*k keys (padding rows -> key 0, the minimum), radix-select the k-th largest, compact the
+// winners into a second array and sort only those (a full bitonic sort of all G*k keys cost 8x the compare-exchanges and
+// made the merge 2.4 ms of a 26 ms step on 8 GPUs).
 __global__ void __launch_bounds__(MERGE_THREADS) merge_topk_kernel(const float* __restrict__ in_scores,
                                                                    const int64_t* __restrict__ in_ids, int32_t n_shards,
                                                                    int32_t n_queries, int32_t k, float* out_scores,
                                                                    int64_t* out_ids, int32_t* out_counts) {
-    extern __shared__ __align__(16) uint64_t skeys[];
+    extern __shared__ __align__(16) uint64_t skeys[];     // [n_shards * k] candidates, then [next_pow2(k)] winners
     __shared__ uint32_t hist[256];
     __shared__ uint64_t bcast[3];
-    __shared__ int n_live;
+    __shared__ int n_live, out_pos;
     const int q = blockIdx.x;
-    if (threadIdx.x == 0) n_live = 0;
-    __syncthreads();
-    // Gather the live (id >= 0) candidates of all shards.  Global ids fit 31 bits (checked on the host).
     const int total = n_shards * k;
+    uint64_t* const wkeys = skeys + total;
+    if (threadIdx.x == 0) {
+        n_live = 0;
+        out_pos = 0;
+    }
+    __syncthreads();
+    // Global ids fit 31 bits (checked on the host).
+    int live = 0;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int g = i / k, j = i % k;
+        const int g = i / k, j = i - g * k;
         const size_t src = (static_cast<size_t>(g) * n_queries + q) * k + j;
         const int64_t id = in_ids[src];
-        if (id >= 0) skeys[atomicAdd(&n_live, 1)] = cand_key(in_scores[src], static_cast<int32_t>(id));
+        skeys[i] = (id >= 0) ? cand_key(in_scores[src], static_cast<int32_t>(id)) : 0ull;
+        live += (id >= 0);
     }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) live += __shfl_xor_sync(0xffffffffu, live, off);
+    if ((threadIdx.x & 31) == 0 && live) atomicAdd(&n_live, live);
     __syncthreads();
     const int c = n_live;
-    int kept = c;
-    uint64_t kth = 0;
-    if (c > k) {
-        kth = block_radix_select_kth(skeys, c, k, hist, bcast);
-        kept = k;
+    const int kept = min(c, k);
+    uint64_t kth = 1;                                     // every live key is >= 1
+    if (c > k) kth = block_radix_select_kth(skeys, total, k, hist, bcast);
+    const int n_sort = next_pow2(max(kept, 1));
+    for (int i0 = 0; i0 < total; i0 += blockDim.x) {      // warp-aggregated compaction of the winners
+        const int i = i0 + threadIdx.x;
+        const uint64_t key = (i < total) ? skeys[i] : 0ull;
+        const bool win = key >= kth;
+        const unsigned bal = __ballot_sync(0xffffffffu, win);
+        if (bal) {
+            int base = 0;
+            if ((threadIdx.x & 31) == 0) base = atomicAdd(&out_pos, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (win) wkeys[base + __popc(bal & lanemask_lt())] = key;
+        }
     }
-    // Keys below the cut become 0 (sorts last); then one descending sort of the padded array.
-    const int n_sort = next_pow2(max(c, 1));
-    for (int i = threadIdx.x; i < n_sort; i += blockDim.x)
-        if (i >= c || skeys[i] < kth) skeys[i] = 0;
-    block_bitonic_sort_desc(skeys, n_sort);
+    for (int i = kept + threadIdx.x; i < n_sort; i += blockDim.x) wkeys[i] = 0;
+    __syncthreads();
+    block_bitonic_sort_desc(wkeys, n_sort);
     for (int i = threadIdx.x; i < k; i += blockDim.x) {
-        const bool live = i < kept;
-        const uint64_t key = live ? skeys[i] : 0;
-        out_scores[static_cast<size_t>(q) * k + i] = live ? cand_score(key) : -INFINITY;
-        out_ids[static_cast<size_t>(q) * k + i] = live ? static_cast<int64_t>(cand_id(key)) : -1;
+        const bool lv = i < kept;
+        const uint64_t key = lv ? wkeys[i] : 0;
+        out_scores[static_cast<size_t>(q) * k + i] = lv ? cand_score(key) : -INFINITY;
+        out_ids[static_cast<size_t>(q) * k + i] = lv ? static_cast<int64_t>(cand_id(key)) : -1;
     }
     if (threadIdx.x == 0) out_counts[q] = kept;
 }
@@ -83,11 +103,11 @@ extern "C" int b200ret_merge_topk(const float* in_scores, const int64_t* in_ids,
                     "merge_topk: n_shards*k=%lld exceeds %d candidates per query", (long long)n_shards * k, MERGE_MAX_CANDIDATES);
     if (n_queries == 0) return B200RET_OK;
     B200RET_REQUIRE(in_scores && in_ids && out_scores && out_ids && out_counts, "merge_topk: null pointer");
-    const size_t smem = static_cast<size_t>(next_pow2(n_shards * k)) * sizeof(uint64_t);
+    const size_t smem = (static_cast<size_t>(n_shards) * k + next_pow2(k)) * sizeof(uint64_t);
     static bool attr_set = false;
     if (!attr_set) {
         B200RET_CUDA_CHECK(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                MERGE_MAX_CANDIDATES * (int)sizeof(uint64_t)));
+                                                (MERGE_MAX_CANDIDATES + B200RET_MAX_K) * (int)sizeof(uint64_t)));
         attr_set = true;
     }
     merge_topk_kernel<<<n_queries, MERGE_THREADS, smem, stream>>>(in_scores, in_ids, n_shards, n_queries, k, out_scores,
