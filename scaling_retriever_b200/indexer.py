@@ -82,6 +82,17 @@ def _stage_out(staging, name, dev_tensor):
 # dense: embeddings dump (unchanged format) + flat inner-product index
 # ------------------------------------------------------------------------------------------------------------------
 
+def _write_emb_chunk(index_dir, local_rank, chunk_idx, embeddings, embeddings_ids, force_int64=False):
+    """embs_{rank}_{chunk}.npy fp32 [n, d] + ids_{rank}_{chunk}.npy (reference indexer.py:58-70; the hybrid indexer always
+    casts the ids to int64, :796)."""
+    embeddings = np.concatenate(embeddings)
+    if force_int64 or isinstance(embeddings_ids[0], int):
+        embeddings_ids = np.array(embeddings_ids, dtype=np.int64)
+    assert len(embeddings) == len(embeddings_ids), (len(embeddings), len(embeddings_ids))
+    np.save(os.path.join(index_dir, "embs_{}_{}.npy".format(local_rank, chunk_idx)), embeddings)
+    np.save(os.path.join(index_dir, "ids_{}_{}.npy".format(local_rank, chunk_idx)), embeddings_ids)
+
+
 def store_embs(model, collection_loader, local_rank, index_dir, device,
                chunk_size=2_000_000, use_fp16=False, is_query=False, idx_to_id=None):
     """Encode the corpus and write embs_{rank}_{chunk}.npy / ids_{rank}_{chunk}.npy / plan.json (reference
@@ -93,12 +104,7 @@ def store_embs(model, collection_loader, local_rank, index_dir, device,
     print("Using bfloat16" if dtype == torch.bfloat16 else "Using float32")
 
     def flush(embeddings, embeddings_ids, chunk_idx):
-        embeddings = np.concatenate(embeddings)
-        if isinstance(embeddings_ids[0], int):
-            embeddings_ids = np.array(embeddings_ids, dtype=np.int64)
-        assert len(embeddings) == len(embeddings_ids), (len(embeddings), len(embeddings_ids))
-        np.save(os.path.join(index_dir, "embs_{}_{}.npy".format(local_rank, chunk_idx)), embeddings)
-        np.save(os.path.join(index_dir, "ids_{}_{}.npy".format(local_rank, chunk_idx)), embeddings_ids)
+        _write_emb_chunk(index_dir, local_rank, chunk_idx, embeddings, embeddings_ids)
 
     embeddings, embeddings_ids, chunk_idx = [], [], 0
     for idx, batch in tqdm(enumerate(collection_loader), disable=not is_first_worker(),
@@ -257,6 +263,35 @@ class DenseFlatIndexer(DenseIndexer):
 # sparse: index build + retrieval
 # ------------------------------------------------------------------------------------------------------------------
 
+def _batch_ids(batch, id_dict=None):
+    if isinstance(batch["ids"], torch.Tensor):
+        batch_ids = to_list(batch["ids"])
+    else:
+        assert isinstance(batch["ids"], list)
+        batch_ids = batch["ids"]
+    if id_dict:
+        batch_ids = [id_dict[x] for x in batch_ids]
+    return batch_ids
+
+
+def _add_sparse_batch(sparse_index, batch_documents, batch_ids, count, world_size, rank, doc_ids, require_all=False):
+    """One encoder batch [bz, V] -> COO postings appended to the GPU-resident log of `sparse_index`, and the row -> external
+    id entries of `doc_ids` (reference indexer.py:259-284 / :776-790): global row = (row + count) * world_size + rank."""
+    row, col = torch.nonzero(batch_documents, as_tuple=True)   # row-major: row asc, col asc
+    data = batch_documents[row, col]
+    g_row = (row + count) * world_size + rank                  # indexer.py:261-262, kept on the device
+    present = torch.zeros(len(batch_ids), dtype=torch.bool, device=row.device)
+    present[row] = True
+    if bool(present.all()):
+        base = count * world_size + rank
+        doc_ids.update({base + i * world_size: y for i, y in enumerate(batch_ids)})
+    else:   # docs without any posting get no doc_ids entry (indexer.py:273-283); the hybrid indexer forbids them (:784)
+        assert not require_all, (int(present.sum()), len(batch_ids))
+        for i in torch.nonzero(present).flatten().tolist():
+            doc_ids[(count + i) * world_size + rank] = batch_ids[i]
+    sparse_index.add_batch_document(g_row, col, data.float(), n_docs=len(batch_ids))
+
+
 class SparseIndexer:
     def __init__(self, model, index_dir, device, compute_stats=False, dim_voc=None, force_new=True,
                  filename="array_index.h5py", **kwargs):
@@ -292,25 +327,8 @@ class SparseIndexer:
                     batch_documents = self.model.encode(**inputs)   # [bz, vocab_size]
                 if self.compute_stats:
                     stats["L0_d"] += self.l0(batch_documents).item()
-                row, col = torch.nonzero(batch_documents, as_tuple=True)   # row-major: row asc, col asc
-                data = batch_documents[row, col]
-                g_row = (row + count) * self.world_size + self.rank         # indexer.py:261-262, kept on the device
-                if isinstance(batch["ids"], torch.Tensor):
-                    batch_ids = to_list(batch["ids"])
-                else:
-                    assert isinstance(batch["ids"], list)
-                    batch_ids = batch["ids"]
-                if id_dict:
-                    batch_ids = [id_dict[x] for x in batch_ids]
-                present = torch.zeros(len(batch_ids), dtype=torch.bool, device=row.device)
-                present[row] = True
-                if bool(present.all()):
-                    base = count * self.world_size + self.rank
-                    doc_ids.update({base + i * self.world_size: y for i, y in enumerate(batch_ids)})
-                else:   # docs without any posting get no doc_ids entry (indexer.py:273-283)
-                    for i in torch.nonzero(present).flatten().tolist():
-                        doc_ids[(count + i) * self.world_size + self.rank] = batch_ids[i]
-                self.sparse_index.add_batch_document(g_row, col, data.float(), n_docs=len(batch_ids))
+                batch_ids = _batch_ids(batch, id_dict)
+                _add_sparse_batch(self.sparse_index, batch_documents, batch_ids, count, self.world_size, self.rank, doc_ids)
                 count += len(batch_ids)
 
         if self.compute_stats:
@@ -506,3 +524,169 @@ class SparseRetrieval:
             with open(os.path.join(self.out_dir, "run.json"), "w") as handler:
                 json.dump(res, handler)
         return res
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# hybrid: one encoder pass -> sparse + dense (reference indexer.py:710-1019), on top of the same two engines
+# ------------------------------------------------------------------------------------------------------------------
+
+class HybridIndexer:
+    """`model.encode` returns (sparse [bz, V], dense [bz, d]); the sparse half goes to the GPU-resident COO log / CSR build of
+    SparseIndexer, the dense half to the embs_/ids_/plan.json shard files of store_embs (reference indexer.py:710-856)."""
+
+    def __init__(self, model, sparse_index_dir, dense_index_dir, device, chunk_size=2_000_000, compute_stats=False,
+                 dim_voc=None, force_new=True, filename="array_index.h5py", **kwargs):
+        self.model = model
+        self.model.eval()
+        self.sparse_index_dir = sparse_index_dir
+        self.dense_index_dir = dense_index_dir
+        self.chunk_size = chunk_size
+        self.device = device
+        self._cuda = _cuda_device(device)
+        self.sparse_index = IndexDictOfArray(self.sparse_index_dir, dim_voc=dim_voc, force_new=force_new, filename=filename,
+                                             device=self._cuda)
+        self.compute_stats = compute_stats
+        if self.compute_stats:
+            self.l0 = L0()
+        self.model.to(self._cuda)
+        self.local_rank = self.device
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            assert self.local_rank == torch.distributed.get_rank(), (self.local_rank, torch.distributed.get_rank())
+        self.rank = _rank()
+        self.world_size = _world_size()
+        print("world_size: {}, local_rank: {}".format(self.world_size, self.local_rank))
+
+    def index(self, collection_loader, id_dict=None):
+        dtype = torch.bfloat16 if supports_bfloat16() else torch.float32
+        print("Using bfloat16" if dtype == torch.bfloat16 else "Using float32")
+        doc_ids = {}
+        stats = defaultdict(float)
+        count = 0
+        embeddings, embeddings_ids, chunk_idx = [], [], 0
+        write_freq = self.chunk_size // collection_loader.batch_size
+        with torch.inference_mode():
+            for idx, batch in enumerate(tqdm(collection_loader, disable=not is_first_worker())):
+                inputs = {k: v.to(self._cuda) for k, v in batch.items() if k not in {"ids"}}
+                with torch.amp.autocast("cuda", dtype=dtype):
+                    batch_sparse_reps, batch_dense_reps = self.model.encode(**inputs)
+                batch_ids = _batch_ids(batch, id_dict)
+                if self.compute_stats:
+                    stats["L0_d"] += self.l0(batch_sparse_reps).item()
+                _add_sparse_batch(self.sparse_index, batch_sparse_reps, batch_ids, count, self.world_size, self.rank, doc_ids,
+                                  require_all=True)
+                count += len(batch_ids)
+                embeddings.append(batch_dense_reps.float().cpu().numpy())
+                embeddings_ids.extend(batch_ids)
+                if (idx + 1) % write_freq == 0:
+                    _write_emb_chunk(self.dense_index_dir, self.local_rank, chunk_idx, embeddings, embeddings_ids, force_int64=True)
+                    embeddings, embeddings_ids = [], []
+                    chunk_idx += 1
+        if len(embeddings) != 0:
+            print("last embedddings shape = {}".format(np.concatenate(embeddings).shape))
+            _write_emb_chunk(self.dense_index_dir, self.local_rank, chunk_idx, embeddings, embeddings_ids, force_int64=True)
+            chunk_idx += 1
+        plan = {"nranks": _world_size(), "num_chunks": chunk_idx, "index_path": os.path.join(self.dense_index_dir, "model.index")}
+        print("plan: ", plan)
+        if is_first_worker():
+            with open(os.path.join(self.dense_index_dir, "plan.json"), "w") as fout:
+                json.dump(plan, fout)
+
+        if self.compute_stats:
+            stats = {key: value / len(collection_loader) for key, value in stats.items()}
+        if self.sparse_index_dir is not None:
+            self.sparse_index.save()
+            pickle.dump(doc_ids, open(os.path.join(self.sparse_index_dir, "doc_ids.pkl"), "wb"))
+            print("done iterating over the corpus...")
+            print("index contains {} posting lists".format(len(self.sparse_index)))
+            print("index contains {} documents".format(len(doc_ids)))
+            if self.compute_stats:
+                with open(os.path.join(self.sparse_index_dir, "index_stats.json"), "w") as handler:
+                    json.dump(stats, handler)
+        else:
+            self.sparse_index.finalize()
+            out = {"index": self.sparse_index, "ids_mapping": doc_ids}
+            if self.compute_stats:
+                out["stats"] = stats
+            return out
+
+
+class HybridRetriever:
+    """One encoder pass per query batch -> sparse run + dense run (reference indexer.py:859-1019).  Both searches run on the
+    GPU engines: the sparse index through SparseRetrieval, the dense shards through DenseFlatIndexer."""
+
+    select_topk = staticmethod(SparseRetrieval.select_topk)
+
+    def __init__(self, model, sparse_index_dir, dense_index_dir, out_dir, dim_voc, device, **kwargs):
+        self.model = model
+        self.model.eval()
+        self.sparse_out_dir = os.path.join(out_dir, "sparse")
+        self.dense_out_dir = os.path.join(out_dir, "dense")
+        if is_first_worker():
+            os.makedirs(self.sparse_out_dir, exist_ok=True)
+            os.makedirs(self.dense_out_dir, exist_ok=True)
+        self.sparse = SparseRetrieval(model, {"index_dir": sparse_index_dir, "out_dir": self.sparse_out_dir}, dim_voc, device)
+        self.sparse_index = self.sparse.sparse_index
+        self.doc_ids = self.sparse.doc_ids
+        self.l0 = L0()
+        self.device = device
+        self._cuda = _cuda_device(device)
+        self.dense_index = DenseFlatIndexer(device=self._cuda)
+        self.dense_index.init_index(self.model.hidden_size)
+        doc_vector_files, doc_id_files = obtain_doc_vec_dir_files(dense_index_dir)
+        self._index_encoded_data(doc_vector_files, doc_id_files)
+        self.model.to(self._cuda)
+
+    def _generate_query_vecs(self, q_loader):
+        sparse_query_vecs, dense_query_vecs, qids = [], [], []
+        with torch.inference_mode():
+            for t, batch in enumerate(tqdm(q_loader, total=len(q_loader), desc="generate query vecs",
+                                           disable=not is_first_worker())):
+                inputs = {k: v.to(self._cuda) for k, v in batch.items() if k not in {"ids"}}
+                with torch.amp.autocast("cuda", dtype=torch.bfloat16 if supports_bfloat16() else torch.float32):
+                    batch_sparse_reps, batch_dense_reps = self.model.encode(**inputs)
+                qids.extend(batch["ids"] if isinstance(batch["ids"], list) else to_list(batch["ids"]))
+                dense_query_vecs.append(batch_dense_reps.float().cpu().numpy())
+                row, col = torch.nonzero(batch_sparse_reps, as_tuple=True)
+                data = batch_sparse_reps[row, col].float().cpu().numpy().astype(np.float32)
+                counts = torch.bincount(row, minlength=batch_sparse_reps.shape[0]).cpu().numpy()
+                col = col.cpu().numpy().astype(np.int32)
+                bounds = np.concatenate([[0], np.cumsum(counts)])
+                for i in range(len(counts)):
+                    sparse_query_vecs.append((col[bounds[i]:bounds[i + 1]], data[bounds[i]:bounds[i + 1]]))
+        dense_query_vecs = np.concatenate(dense_query_vecs, axis=0)
+        assert len(sparse_query_vecs) == len(dense_query_vecs) == len(qids), (len(sparse_query_vecs), len(dense_query_vecs), len(qids))
+        return sparse_query_vecs, dense_query_vecs, qids
+
+    def _index_encoded_data(self, doc_vec_files, doc_id_files):
+        doc_reps = np.concatenate([np.load(f) for f in doc_vec_files], axis=0)
+        doc_ids = np.concatenate([np.load(f) for f in doc_id_files]).tolist()
+        assert len(doc_reps) == len(doc_ids), (len(doc_reps), len(doc_ids))
+        print("size of doc reps to index: ", doc_reps.shape)
+        self.dense_index.index_data(doc_reps, doc_ids)
+        print("finished indexing")
+
+    def _dense_retrieve(self, query_reps, qids, topk=1000):
+        res = defaultdict(dict)
+        top_doc_ids, top_scores = self.dense_index.search_knn(query_reps, topk)
+        assert len(qids) == len(query_reps), (len(qids), len(query_reps))
+        for qid, docids, scores in zip(qids, top_doc_ids, top_scores.astype(float).tolist()):
+            res[str(qid)].update(zip(map(str, docids), scores))
+        return res
+
+    def _sparse_retrieve(self, sparse_query_vecs, qids, threshold=0., topk=1000):
+        return self.sparse._sparse_retrieve_multithreaded(sparse_query_vecs, qids, threshold=threshold, topk=topk)
+
+    def retrieve(self, q_loader, topk, id_dict=False, threshold=0.):
+        """Writes sparse/q_stats.json, sparse/run.json and dense/run.json like the reference; additionally returns the two
+        result dicts (the reference returns None)."""
+        sparse_query_vecs, dense_query_vecs, qids = self._generate_query_vecs(q_loader)
+        sparse_res, sparse_stats = self._sparse_retrieve(sparse_query_vecs, qids, threshold=threshold, topk=topk)
+        dense_res = self._dense_retrieve(dense_query_vecs, qids, topk=topk)
+        if is_first_worker():
+            with open(os.path.join(self.sparse_out_dir, "q_stats.json"), "w") as handler:
+                json.dump(sparse_stats, handler)
+            with open(os.path.join(self.sparse_out_dir, "run.json"), "w") as handler:
+                json.dump(sparse_res, handler)
+            with open(os.path.join(self.dense_out_dir, "run.json"), "w") as handler:
+                json.dump(dense_res, handler)
+        return sparse_res, dense_res

@@ -178,3 +178,70 @@ def test_dense_store_embs_then_search_knn(cuda, tmp_path):
     for a, b, s in zip(top_ids, o_ids, o_scores):
         assert len(set(a) & set(b)) >= k - 2          # near-ties at the k boundary may swap
         assert a[0] == b[0] or abs(s[0] - s[1]) < 1e-5
+
+
+class FakeHybridEncoder(torch.nn.Module):
+    """Stands in for the hybrid Llama encoder: encode(input_ids=rows) -> (sparse [bz, V], dense [bz, d])."""
+
+    def __init__(self, sparse_table, dense_table):
+        super().__init__()
+        self.register_buffer("sparse_table", sparse_table)
+        self.register_buffer("dense_table", dense_table)
+        self.vocab_size = sparse_table.shape[1]
+        self.hidden_size = dense_table.shape[1]
+
+    def encode(self, input_ids):
+        return self.sparse_table[input_ids], self.dense_table[input_ids]
+
+
+def test_hybrid_index_then_retrieve_equals_the_two_single_paths(golden, cuda, tmp_path):
+    """HybridIndexer / HybridRetriever (reference indexer.py:710-1019): one encoder pass feeds both engines; the sparse run
+    must equal SparseRetrieval's over the same index directory and the dense run DenseFlatIndexer's over the same shard
+    files (both single paths are pinned against the reference golden run / the oracle above)."""
+    from scaling_retriever.indexer import HybridIndexer, HybridRetriever
+    off, ids, vals = golden["C_offsets"], golden["C_ids"], golden["C_vals"]
+    n_docs, n_terms, d = int(golden["C_n_docs"]), int(golden["C_n_terms"]), 64
+    sparse_docs = dense_from_csr(off, ids, vals, n_docs)
+    sparse_docs[:, 0] += (sparse_docs.sum(dim=1) == 0).float()      # the hybrid indexer requires a posting for every doc
+    g = torch.Generator().manual_seed(3)
+    dense_docs = torch.nn.functional.normalize(torch.randn(n_docs, d, generator=g), dim=1)
+    ext_ids = [1000 + 3 * i for i in range(n_docs)]                  # int ids: the hybrid dense shards are int64 (:796)
+    sparse_dir, dense_dir, out_dir = str(tmp_path / "sparse_index"), str(tmp_path / "dense_index"), str(tmp_path / "out")
+    for p in (sparse_dir, dense_dir, out_dir):
+        os.makedirs(p)
+
+    indexer = HybridIndexer(FakeHybridEncoder(sparse_docs, dense_docs), sparse_dir, dense_dir, device=0, chunk_size=64 * 20,
+                            compute_stats=True, dim_voc=n_terms)
+    assert indexer.index(make_loader(n_docs, ext_ids)) is None
+    with open(os.path.join(dense_dir, "plan.json")) as f:
+        plan = json.load(f)
+    assert plan["nranks"] == 1 and plan["num_chunks"] == -(-n_docs // (64 * 20))
+    vec_files, id_files = obtain_doc_vec_dir_files(dense_dir)
+    assert np.concatenate([np.load(f) for f in id_files]).tolist() == ext_ids
+    assert pickle.load(open(os.path.join(sparse_dir, "doc_ids.pkl"), "rb"))[2] == ext_ids[2]
+
+    q_off, q_t, q_w = golden["C_q_offsets"], golden["C_q_terms"], golden["C_q_weights"]
+    nq = len(q_off) - 1
+    sparse_q = torch.zeros((nq, n_terms))
+    for i in range(nq):
+        sparse_q[i, torch.as_tensor(q_t[q_off[i]:q_off[i + 1]].astype(np.int64))] = torch.as_tensor(q_w[q_off[i]:q_off[i + 1]])
+    dense_q = torch.nn.functional.normalize(torch.randn(nq, d, generator=g), dim=1)
+    qids = [f"q{i}" for i in range(nq)]
+    topk = 50
+    retriever = HybridRetriever(FakeHybridEncoder(sparse_q, dense_q), sparse_dir, dense_dir, out_dir, n_terms, 0)
+    sparse_res, dense_res = retriever.retrieve(make_loader(nq, qids, bs=7), topk=topk)
+    for sub in ("sparse/run.json", "sparse/q_stats.json", "dense/run.json"):
+        assert os.path.exists(os.path.join(out_dir, sub)), sub
+    with open(os.path.join(out_dir, "dense", "run.json")) as f:
+        assert json.load(f) == json.loads(json.dumps(dense_res))
+
+    single_out = str(tmp_path / "single")
+    os.makedirs(single_out)
+    single = SparseRetrieval(FakeSparseEncoder(sparse_q), {"index_dir": sparse_dir, "out_dir": single_out}, n_terms, 0)
+    assert single.retrieve(make_loader(nq, qids, bs=7), topk=topk) == sparse_res
+    dense_index = DenseFlatIndexer()
+    dense_index.init_index(d)
+    dense_index.index_data(np.concatenate([np.load(f) for f in vec_files], axis=0), ext_ids)
+    top_ids, top_scores = dense_index.search_knn(dense_q.numpy(), topk)
+    for qid, docids, scores in zip(qids, top_ids, top_scores):
+        assert dense_res[qid] == {str(a): float(b) for a, b in zip(docids, scores)}
