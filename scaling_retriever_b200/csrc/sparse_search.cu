@@ -17,14 +17,16 @@
 //   * The streaming loop walks a warp-uniform cursor over 256-byte aligned rows of 32 postings (one posting per
 //     lane, one predicated coalesced 64-bit load of {doc id, weight}), STEP_ROWS rows of one slice per step; the
 //     slice descriptors (begin, end, query weight) of a group of 32 query terms sit in a small warp-private
-//     shared array.  PIPE_DEPTH steps are kept in flight in a register ring (fetch step i+DEPTH-1, then consume
-//     step i).  The ring NEVER drains: the fetch side runs ahead of the accumulate side across term groups AND
-//     across work items.  Its inputs come from a software pipeline of their own, advanced once per term group:
-//     item claim (atomic) -> q_offsets of that item -> term ids / weights of a group -> skip-table entries of the
-//     group -> descriptors in shared memory, each stage issued one group before its result is needed.  The end
-//     of an item travels through the ring as a marker step; the accumulate side sweeps the tile when it meets it.
-//   * Sweep: 128-bit shared loads, zeroing as it goes; documents with score > tau[q] are appended to the
-//     query's candidate list (candidates.cuh: rounds of growing size, radix-select cut to k between rounds,
+//     shared array.  Steps are loaded in two register batches, double-buffered: the loads of one batch are in flight
+//     while the other is accumulated (all posting loads of a warp share one hardware scoreboard, so the order
+//     wait -> issue -> accumulate is pinned with a data dependency; see the main loop).  The load pipeline NEVER
+//     drains: the fetch side runs ahead of the accumulate side across term groups AND across work items.  Its inputs
+//     come from a software pipeline of their own, advanced once per term group: item claim (atomic) -> q_offsets of
+//     that item -> term ids / weights of a group -> skip-table entries of the group -> descriptors in shared memory,
+//     each stage an asynchronous copy issued one group before its result is needed.
+//   * Sweep (end of an item): one pass over the tile that zeroes everything but the hits (score > tau[q]) and records
+//     them in per-lane bit masks, one atomic that reserves the item's slots in the query's candidate list, then
+//     every lane emits its hits (candidates.cuh: rounds of growing size, radix-select cut to k between rounds,
 //     overflow -> safe re-run).
 #include "candidates.cuh"
 
@@ -39,20 +41,10 @@ constexpr int ROUND0_BLOCKS = B200RET_ROUND0_BLOCKS;   // first round / safe-sch
 #ifndef B200RET_LDNC           // posting-load flavour (tuning knob)
 #define B200RET_LDNC "ld.global.nc"
 #endif
-#ifndef B200RET_SKIP_EMPTY      // branch around the accumulate of an empty step (else it runs fully predicated off)
-#define B200RET_SKIP_EMPTY 1
-#endif
-#ifndef B200RET_RING_CHECKS     // control points per revolution of the register ring (1 or 2)
-#define B200RET_RING_CHECKS 1      // 2 measured slower (124.2 vs 119.2 ms per step): the second copy of the control code costs more than the empty steps it saves
-#endif
-#ifndef B200RET_BATCH_STEPS     // > 0: two double-buffered register batches of this many steps instead of the ring
+#ifndef B200RET_BATCH_STEPS     // steps per register batch (two batches, double-buffered); 2 and 3 measure equal
 #define B200RET_BATCH_STEPS 2
 #endif
-#ifndef B200RET_PIPE_DEPTH
-#define B200RET_PIPE_DEPTH 5
-#endif
 constexpr int STEP_ROWS = 4;                     // rows (of 32 postings) fetched per pipeline step
-constexpr int PIPE_DEPTH = B200RET_PIPE_DEPTH;   // steps in flight per warp (register ring)
 
 // Kernel shape: one CTA of WARPS warps per SM, BD docs per warp-private score tile (BD * 4 bytes of shared memory).
 constexpr int SCORE_WARPS = B200RET_SCORE_WARPS;
@@ -380,47 +372,8 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
     // read-modify-writes are independent: loads, adds and stores are issued R-wide (one latency per step).
     // reference arithmetic: scores[doc] += q * w  -> fp32 multiply, then fp32 add (no FMA).
     // acc_rel_s: shared-memory byte address such that acc_rel_s + 4 * doc_id is the doc's score slot.
-    auto consume = [&](const int (&id)[R], const float (&w)[R], float qw, unsigned rel, unsigned len, uint32_t acc_rel_s) {
-        static_assert(R == 4, "the fetch/accumulate blocks are written for 4 rows per step");
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p0, p1, p2, p3;\n\t"
-            ".reg .f32 a0, a1, a2, a3, v0, v1, v2, v3;\n\t"
-            ".reg .u32 d0, d1, d2, d3, t1, t2, t3;\n\t"
-            "add.u32 t1, %9, 32;\n\t"
-            "add.u32 t2, %9, 64;\n\t"
-            "add.u32 t3, %9, 96;\n\t"
-            "setp.lt.u32 p0, %9, %10;\n\t"
-            "setp.lt.u32 p1, t1, %10;\n\t"
-            "setp.lt.u32 p2, t2, %10;\n\t"
-            "setp.lt.u32 p3, t3, %10;\n\t"
-            "mad.lo.u32 d0, %0, 4, %11;\n\t"
-            "mad.lo.u32 d1, %1, 4, %11;\n\t"
-            "mad.lo.u32 d2, %2, 4, %11;\n\t"
-            "mad.lo.u32 d3, %3, 4, %11;\n\t"
-            "@p0 ld.shared.f32 a0, [d0];\n\t"
-            "@p1 ld.shared.f32 a1, [d1];\n\t"
-            "@p2 ld.shared.f32 a2, [d2];\n\t"
-            "@p3 ld.shared.f32 a3, [d3];\n\t"
-            "mul.rn.f32 v0, %8, %4;\n\t"
-            "mul.rn.f32 v1, %8, %5;\n\t"
-            "mul.rn.f32 v2, %8, %6;\n\t"
-            "mul.rn.f32 v3, %8, %7;\n\t"
-            "@p0 add.rn.f32 a0, a0, v0;\n\t"
-            "@p1 add.rn.f32 a1, a1, v1;\n\t"
-            "@p2 add.rn.f32 a2, a2, v2;\n\t"
-            "@p3 add.rn.f32 a3, a3, v3;\n\t"
-            "@p0 st.shared.f32 [d0], a0;\n\t"
-            "@p1 st.shared.f32 [d1], a1;\n\t"
-            "@p2 st.shared.f32 [d2], a2;\n\t"
-            "@p3 st.shared.f32 [d3], a3;\n\t"
-            "}\n" ::"r"(id[0]), "r"(id[1]), "r"(id[2]), "r"(id[3]), "f"(w[0]), "f"(w[1]), "f"(w[2]), "f"(w[3]), "f"(qw),
-            "r"(rel), "r"(len), "r"(acc_rel_s)
-            : "memory");
-        __syncwarp();   // orders this step's shared-memory updates before the next step (possibly the next term)
-    };
-    // The same accumulate in two parts: the score-slot addresses (first use of the loaded doc ids: the scoreboard wait for
-    // the batch's loads happens here), and the read-modify-writes.
+    // In two parts: the score-slot addresses (first use of the loaded doc ids: the scoreboard wait for the batch's loads
+    // happens here), and the read-modify-writes.
     auto consume_pre = [&](const int (&id)[R], uint32_t (&d)[R], uint32_t acc_rel_s) {
         asm volatile(
             "mad.lo.u32 %0, %4, 4, %8;\n\t"
@@ -463,11 +416,6 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
             : "memory");
         __syncwarp();
     };
-    (void)consume;
-    (void)consume_pre;
-    (void)consume_rest;
-
-#if B200RET_BATCH_STEPS > 0
     // Two register batches of HB steps each, double-buffered: all posting loads of a warp share ONE hardware scoreboard
     // (ptxas gives the other five to the shared-memory loads), so "wait for this step's loads" means "wait for every load in
     // flight".  A ring that fetches one step per consumed step therefore exposes the full load latency again and again (ptxas
@@ -550,91 +498,6 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
         half(HB, 0);
     }
 }
-#else
-    // S steps in flight in a register ring: consume step i, then fetch step i+S into the freed slot.  The ring indices are
-    // compile-time constants after unrolling, so the slots stay in registers.  All control work happens at the boundary
-    // between two revolutions of the ring (one copy of the cold code, no calls, nothing in the hot loop but the steps):
-    //   * when the cursor has exhausted its term group, the remaining fetches of the revolution return empty steps
-    //     (len == 0); at the boundary the next group is installed and the input pipeline moves one stage forward;
-    //   * if that group was the item's last, the item's steps were all fetched before this boundary, so they are all
-    //     consumed during the coming revolution: its tile is swept one revolution later (sweep_cd), before the first step
-    //     of the following item (fetched during the coming revolution) is consumed.
-    constexpr int S = PIPE_DEPTH;
-    int id[S][R];
-    float w[S][R], qw[S];
-    unsigned rel[S], len[S];
-#pragma unroll
-    for (int s = 0; s < S; ++s) len[s] = 0u;
-    FetchStages fs(p, ctrl, lane);
-    uint32_t acc_rel_s = acc_s - static_cast<uint32_t>(st.a_blk * BD) * 4u;   // tile base of the first item (group a)
-    // Control points: CHECKS per revolution (before body 0 and, with 2, before body S/2 + 1).  Whatever their spacing, the S
-    // steps in the ring at a control point are consumed exactly CHECKS control points later: countdowns in control points.
-    constexpr int CHECKS = B200RET_RING_CHECKS;
-    constexpr int MID = S / 2 + 1;
-    int sweep_cd = 0, fin_cd = 0;
-    int sw_q = 0, sw_doc_base = 0;
-    float sw_tau = 0.f;
-    uint32_t sw_next_acc_rel = 0;
-    auto control = [&]() -> bool {      // returns false when the warp is done
-        if (sweep_cd != 0 && --sweep_cd == 0) {
-            sweep_tile(p, acc, sw_q, sw_doc_base, sw_tau, lane);
-            acc_rel_s = sw_next_acc_rel;
-        }
-        if (fin_cd != 0) return --fin_cd != 0;
-        while (pending == 0u && c_row >= c_end) {             // group exhausted: warp-uniform, once per term group
-            unsigned flags = st.flags;
-            if ((flags & (K_VALID | K_LAST | K_MARKED)) == (K_VALID | K_LAST)) {   // the item is complete in the ring: close it
-                if (sweep_cd != 0) break;                     // (an item without postings right behind: one sweep at a time)
-                fs.st.flags = flags | K_MARKED;
-                flags |= K_MARKED;
-                sweep_cd = CHECKS;
-                sw_q = st.k_q;
-                sw_doc_base = st.k_blk * BD;
-                sw_tau = p.tau ? __ldg(p.tau + sw_q) : 0.f;   // arrives while the item's last steps are consumed
-                sw_next_acc_rel = acc_s - static_cast<uint32_t>(((flags & A_VALID) ? st.a_blk : st.k_blk) * BD) * 4u;
-            }
-            if (!(flags & A_VALID)) {
-                fin_cd = CHECKS;
-                break;
-            }
-            // install group a (its skip-table entries were requested one group ago), then move the stages forward
-            cp_async_wait_all();
-            __syncwarp();
-            const unsigned gen = st.gen;
-            const uint32_t* buf = ctrl + CTRL_DESC + (gen & 1u) * 96;
-            pending = __ballot_sync(FULL, buf[32 + lane] > buf[lane]);   // non-empty slices, ascending term order
-            desc_s = desc_s01 - desc_s;                       // the cursor reads slice j's descriptor with 3 broadcast LDS.32
-            fs.st.k_q = st.a_q;
-            fs.st.k_blk = st.a_blk;
-            flags = (flags & ~(K_VALID | K_LAST | K_MARKED)) | K_VALID | ((flags & A_LAST) ? K_LAST : 0u);
-            fs.want_claim = false;
-            fs.stage_table(flags, ctrl + CTRL_DESC + ((gen + 1u) & 1u) * 96);
-            fs.stage_terms(flags, __shfl_sync(FULL, nn_item, 0));
-            fs.st.gen = gen + 1u;
-            fs.st.flags = flags;
-            if (fs.want_claim && lane == 0) nn_item = atomicAdd(p.item_counter, 1u);   // stays in flight
-        }
-        return true;
-    };
-    bool running = true;
-    while (running) {
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-            if (s == 0 || (CHECKS == 2 && s == MID)) {
-                if (!control()) {
-                    running = false;
-                    break;
-                }
-            }
-#if B200RET_SKIP_EMPTY
-            if (len[s] != 0u)
-#endif
-                consume(id[s], w[s], qw[s], rel[s], len[s], acc_rel_s);
-            fetch(id[s], w[s], qw[s], rel[s], len[s], 0);
-        }
-    }
-}
-#endif
 
 static int block_docs_of_shape() { return BLOCK_DOCS; }
 
