@@ -248,6 +248,11 @@ dense_search_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             uint64_t* cq = p.cand + static_cast<size_t>(q_live ? q : 0) * p.cap;
             mbar_wait(smem_u32(tmem_full_bar + acc), acc_phase);
             tc_fence_after();
+            // Pass 0 (every tile): row maximum vs tau.  Only if some row of the warp has a hit: count the row's hits, reserve
+            // its candidate slots with ONE atomic per row, then emit.  (One atomic per hit serialised ~1 us round trips: with
+            // tau still low in the first rounds a tile's epilogue took 20x its MMA time — a fixed cost per shard that
+            // dominated small shards.)  tcgen05.ld is warp-collective, so the extra passes are taken warp-uniformly.
+            bool any = false;
 #pragma unroll 1
             for (int c = 0; c < D_BLOCK_N / 32; ++c) {
                 uint32_t v[32];
@@ -255,14 +260,32 @@ dense_search_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 float m = -INFINITY;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
-                if (m > tq) {   // rare after the first rounds
+                any |= m > tq;
+            }
+            if (__any_sync(0xffffffffu, any)) {
+                const int32_t live_cols = p.doc_end - doc0;      // columns >= live_cols are past the end of the shard
+                int cnt = 0;
+#pragma unroll 1
+                for (int c = 0; c < D_BLOCK_N / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_load_32cols(tmem_base + ((ew * 32u) << 16) + acc * D_BLOCK_N + c * 32, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) cnt += (__uint_as_float(v[j]) > tq && c * 32 + j < live_cols) ? 1 : 0;
+                }
+                int pos = 0;
+                if (cnt > 0) pos = atomicAdd(p.cand_count + q, cnt);
+                if (__any_sync(0xffffffffu, cnt > 0)) {
+#pragma unroll 1
+                    for (int c = 0; c < D_BLOCK_N / 32; ++c) {
+                        uint32_t v[32];
+                        tmem_load_32cols(tmem_base + ((ew * 32u) << 16) + acc * D_BLOCK_N + c * 32, v);
 #pragma unroll              // static register indices: v[] must not be demoted to local memory
-                    for (int j = 0; j < 32; ++j) {
-                        const float s = __uint_as_float(v[j]);
-                        const int32_t doc = doc0 + c * 32 + j;
-                        if (s > tq && doc < p.doc_end) {
-                            const int pos = atomicAdd(p.cand_count + q, 1);
-                            if (pos < p.cap) cq[pos] = cand_key(s, doc);
+                        for (int j = 0; j < 32; ++j) {
+                            const float sc = __uint_as_float(v[j]);
+                            if (sc > tq && c * 32 + j < live_cols) {
+                                if (pos < p.cap) cq[pos] = cand_key(sc, doc0 + c * 32 + j);
+                                ++pos;
+                            }
                         }
                     }
                 }
