@@ -28,6 +28,8 @@
 //     them in per-lane bit masks, one atomic that reserves the item's slots in the query's candidate list, then
 //     every lane emits its hits (candidates.cuh: rounds of growing size, radix-select cut to k between rounds,
 //     overflow -> safe re-run).
+#include <cstdlib>
+
 #include "candidates.cuh"
 
 namespace b200ret {
@@ -510,7 +512,9 @@ static int launch_score(const ScoreParams& sp, cudaStream_t stream) {
     }
     // The item counter is 32 bits wide (claims run past the end by a few per warp): cut the block range so that one
     // launch hands out < 2^31 (query, block) items.
-    const int max_blocks = std::max(1, static_cast<int>(((1u << 31) - (1u << 20)) / static_cast<unsigned>(std::max(sp.n_active, 1))));
+    unsigned max_items = (1u << 31) - (1u << 20);
+    if (const char* e = getenv("B200RET_TEST_MAX_ITEMS")) max_items = std::max(1u, static_cast<unsigned>(atoi(e)));   // test hook
+    const int max_blocks = std::max(1, static_cast<int>(max_items / static_cast<unsigned>(std::max(sp.n_active, 1))));
     B200RET_REQUIRE(sp.n_active < (1 << 30), "sparse: %d queries in one launch", sp.n_active);
     for (int b0 = sp.blk_begin; b0 < sp.blk_end; b0 += max_blocks) {
         ScoreParams r = sp;

@@ -295,3 +295,20 @@ def test_search_doc_id_base_and_empty_inputs(cuda):
 def test_ops_reject_cpu_tensors():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.csr_build(torch.zeros(1, dtype=torch.int32), torch.zeros(1, dtype=torch.int32), torch.zeros(1), 4, 1)
+
+
+def test_search_item_range_chunking(cuda, monkeypatch):
+    """The kernel's item counter is 32 bits wide; launch_score cuts the doc-block range into launches of < 2^31 items.  The
+    test hook lowers that limit so that every round is cut into many launches: results must not change."""
+    n_docs, n_terms, k = 3328 * 23 + 5, 2000, 100
+    rows, cols, vals = synth.gen_sparse_docs(n_docs, n_terms=n_terms, mean_nnz=20, seed=13, device=cuda)
+    index = ops.SparseDeviceIndex.from_coo(rows, cols, vals, n_terms, n_docs)
+    q_off, q_t, q_w = synth.gen_sparse_queries(50, n_terms=n_terms, mean_nnz=20, seed=14, device=cuda)
+    ref = ops.sparse_search(index, q_off, q_t, q_w, k, 0.0)
+    monkeypatch.setenv("B200RET_TEST_MAX_ITEMS", "120")          # 50 queries -> 2 doc blocks per launch
+    cut = ops.sparse_search(index, q_off, q_t, q_w, k, 0.0)
+    for a, b in zip(ref, cut):
+        assert torch.equal(a, b)
+    dense_ref = ops.sparse_scores(index, q_off, q_t, q_w)
+    monkeypatch.delenv("B200RET_TEST_MAX_ITEMS")
+    assert torch.equal(dense_ref, ops.sparse_scores(index, q_off, q_t, q_w))
