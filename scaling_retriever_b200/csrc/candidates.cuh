@@ -15,7 +15,10 @@
 namespace b200ret {
 
 constexpr int SELECT_THREADS = 512;
-constexpr int ROUND_GROWTH = 4;   // total docs scored grow 4x per round (4, 16, 64, ... units)
+#ifndef B200RET_ROUND_GROWTH
+#define B200RET_ROUND_GROWTH 4
+#endif
+constexpr int ROUND_GROWTH = B200RET_ROUND_GROWTH;   // total docs scored grow 4x per round (4, 16, 64, ... units)
 
 struct CandBuffers {
     uint64_t* cand;        // [n_queries][cap] keys (cand_key)
