@@ -200,31 +200,39 @@ struct FetchStages {
             want_claim = true;
         }
     }
+    // The stash is shared by the 32 lanes of the warp, which all execute this code with the same values.  Every stage reads
+    // what it needs into registers, then __syncwarp(), then writes: no lane can overwrite a field another lane has yet to read.
+
     // b <- the group after b: issue its term-id and query-weight copies (requires n's q_offsets to have landed)
     __device__ __forceinline__ void stage_terms(unsigned& flags, unsigned nn_item) {
-        int g, qe;
-        if ((flags & (B_VALID | B_LAST)) == B_VALID) {
+        const bool next_group = (flags & (B_VALID | B_LAST)) == B_VALID;      // same item, next 32 terms
+        const bool next_item = !next_group && (flags & N_VALID);
+        int g = 0, qe = 0, n_q = 0, n_blk = 0;
+        if (next_group) {
             g = st.b_g + 32;
             qe = st.b_qe;
-        } else if (flags & N_VALID) {
-            st.b_q = st.n_q;
-            st.b_blk = st.n_blk;
+        } else if (next_item) {
+            n_q = st.n_q;
+            n_blk = st.n_blk;
             g = st.n_qb;
             qe = st.n_qe;
+        }
+        __syncwarp();
+        if (next_item) {
+            st.b_q = n_q;
+            st.b_blk = n_blk;
             st.b_qe = qe;
             flags |= B_VALID;
-            __syncwarp();                 // every lane has read n_qb / n_qe before lane 0 re-targets them
-            stage_item(flags, nn_item);
-        } else {
+            stage_item(flags, nn_item);       // re-targets n_q / n_blk / n_qb / n_qe
+        } else if (!next_group) {
             flags &= ~B_VALID;
-            g = qe = 0;
         }
         st.b_g = g;
         flags &= ~B_LAST;
         int32_t* tb_t = reinterpret_cast<int32_t*>(ctrl + CTRL_TERMS);
         float* tb_w = reinterpret_cast<float*>(ctrl + CTRL_TERMS + 32);
         if ((flags & B_VALID) && g + 32 >= qe) flags |= B_LAST;
-        if ((flags & B_VALID) && g + static_cast<int>(lane) < qe) {
+        if ((flags & B_VALID) && g + static_cast<int>(lane) < qe) {      // lane-private staging slots
             cp_async4(tb_t + lane, p.q_terms + g + lane);
             cp_async4(tb_w + lane, p.q_weights + g + lane);
         } else {
@@ -235,12 +243,14 @@ struct FetchStages {
     // a <- b: issue the two skip-table copies of every term of the group into descriptor buffer `buf` (requires b's term
     // ids to have landed)
     __device__ __forceinline__ void stage_table(unsigned& flags, uint32_t* buf) {
-        const int blk = st.b_blk;
-        st.a_q = st.b_q;
+        const int blk = st.b_blk, bq = st.b_q;
+        const int t = reinterpret_cast<const int32_t*>(ctrl + CTRL_TERMS)[lane];
+        const uint32_t qw_bits = ctrl[CTRL_TERMS + 32 + lane];
+        __syncwarp();
+        st.a_q = bq;
         st.a_blk = blk;
         flags = (flags & ~(A_VALID | A_LAST)) | ((flags & B_VALID) ? A_VALID : 0u) | ((flags & B_LAST) ? A_LAST : 0u);
-        const int t = reinterpret_cast<const int32_t*>(ctrl + CTRL_TERMS)[lane];
-        buf[64 + lane] = ctrl[CTRL_TERMS + 32 + lane];     // query weight
+        buf[64 + lane] = qw_bits;     // query weight
         if ((flags & A_VALID) && t >= 0) {
             const uint32_t* e = p.table + static_cast<size_t>(t) * p.table_stride + blk;
             cp_async4(buf + lane, e);
@@ -277,6 +287,7 @@ __device__ __forceinline__ unsigned prime_pipeline(const ScoreParams& p, uint32_
     fs.stage_terms(flags, nn);                // b <- the second group
     if (fs.want_claim) claim();
     fs.st.flags = flags;
+    __syncwarp();
     return nn;
 }
 
@@ -462,13 +473,14 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
             unsigned flags = st.flags;
             if ((flags & (K_VALID | K_LAST | K_MARKED)) == (K_VALID | K_LAST)) {   // the item is complete (its last steps are in A)
                 if (sweep_due) break;                         // (an item without postings right behind: one sweep per iteration)
-                fs.st.flags = flags | K_MARKED;
-                flags |= K_MARKED;
                 sweep_due = true;
                 sw_q = st.k_q;
                 sw_doc_base = st.k_blk * BD;
                 sw_tau = p.tau ? __ldg(p.tau + sw_q) : 0.f;   // arrives while A is accumulated
                 sw_next_acc_rel = acc_s - static_cast<uint32_t>(((flags & A_VALID) ? st.a_blk : st.k_blk) * BD) * 4u;
+                flags |= K_MARKED;
+                __syncwarp();                                 // stash: reads above, write below
+                fs.st.flags = flags;
             }
             if (!(flags & A_VALID)) {
                 fin = true;                                   // A is still accumulated (and swept) in this iteration
@@ -478,17 +490,20 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
             cp_async_wait_all();
             __syncwarp();
             const unsigned gen = st.gen;
+            const int a_q = st.a_q, a_blk = st.a_blk;
             const uint32_t* buf = ctrl + CTRL_DESC + (gen & 1u) * 96;
             pending = __ballot_sync(FULL, buf[32 + lane] > buf[lane]);   // non-empty slices, ascending term order
             desc_s = desc_s01 - desc_s;                       // the cursor reads slice j's descriptor with 3 broadcast LDS.32
-            fs.st.k_q = st.a_q;
-            fs.st.k_blk = st.a_blk;
+            __syncwarp();                                     // stash: reads above, writes below
+            fs.st.k_q = a_q;
+            fs.st.k_blk = a_blk;
             flags = (flags & ~(K_VALID | K_LAST | K_MARKED)) | K_VALID | ((flags & A_LAST) ? K_LAST : 0u);
             fs.want_claim = false;
             fs.stage_table(flags, ctrl + CTRL_DESC + ((gen + 1u) & 1u) * 96);
             fs.stage_terms(flags, __shfl_sync(FULL, nn_item, 0));
             fs.st.gen = gen + 1u;
             fs.st.flags = flags;
+            __syncwarp();   // the stash is written by every lane with the same values; order them before the next reads
             if (fs.want_claim && lane == 0) nn_item = atomicAdd(p.item_counter, 1u);   // stays in flight
         }
         half(0, HB);
