@@ -37,7 +37,7 @@ namespace b200ret {
 #ifndef B200RET_SCORE_WARPS     // kernel shape (tuning knobs): warps per CTA, docs per warp tile, blocks in round 0
 #define B200RET_SCORE_WARPS 16
 #define B200RET_BLOCK_DOCS 3328
-#define B200RET_ROUND0_BLOCKS 4
+#define B200RET_ROUND0_BLOCKS 2
 #endif
 constexpr int ROUND0_BLOCKS = B200RET_ROUND0_BLOCKS;   // first round / safe-schedule round size, in doc blocks
 #ifndef B200RET_LDNC           // posting-load flavour (tuning knob)
