@@ -92,12 +92,11 @@ int launch_select(bool final, const CandBuffers& b, int32_t cap, int32_t k, int3
                          const int32_t* q_list, int64_t doc_id_base, float* out_scores, int64_t* out_ids, int32_t* out_counts,
                          cudaStream_t stream) {
     const size_t smem = static_cast<size_t>(cap) * sizeof(uint64_t);
-    static bool attrs_set = false;
-    if (!attrs_set) {
+    static PerDeviceOnce attrs_set;
+    if (attrs_set.first()) {
         const int max_smem = 200 * 1024;
         B200RET_CUDA_CHECK(cudaFuncSetAttribute(select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         B200RET_CUDA_CHECK(cudaFuncSetAttribute(select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        attrs_set = true;
     }
     if (smem > 200 * 1024) {
         set_err("select: candidate capacity %d needs %zu bytes of shared memory", cap, smem);

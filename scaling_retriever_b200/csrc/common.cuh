@@ -51,6 +51,18 @@ struct Workspace {
 
 int sm_count();
 
+// One-time per-device setup (kernel attributes are per context): `if (once.first()) cudaFuncSetAttribute(...)`.
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool first() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+        if (done[dev]) return false;
+        done[dev] = true;
+        return true;
+    }
+};
+
 // Launch accounting / optional per-kernel CUDA-event timing on the launching stream (see b200ret_profile_*).
 constexpr int PROF_KINDS = 4;
 constexpr int PROF_SPARSE_SCORE = 0, PROF_SPARSE_SELECT = 1, PROF_DENSE_GEMM = 2, PROF_CSR_SORT = 3;

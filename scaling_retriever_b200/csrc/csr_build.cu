@@ -482,11 +482,10 @@ extern "C" int b200ret_csr_build(const int32_t* rows, const int32_t* cols, const
     int64_t per_block = (nnz + grid - 1) / grid;
     per_block = (per_block + SORT_TILE - 1) / SORT_TILE * SORT_TILE;
 
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.first()) {
         B200RET_CUDA_CHECK(cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 static_cast<int>(SORT_SCATTER_SMEM)));
-        attr_set = true;
     }
     const PassPlan plan = make_plan(n_terms, n_docs, sort_docs);
     const int32_t* src_row = rows;
@@ -559,10 +558,9 @@ extern "C" int b200ret_sparse_layout(const uint32_t* table, const int32_t* doc_i
     if (n_blocks == 0 || nnz == 0) return B200RET_OK;
     B200RET_REQUIRE(doc_ids && weights && postings_out, "sparse_layout: null pointer");
     B200RET_REQUIRE(reinterpret_cast<uintptr_t>(postings_out) % 8 == 0, "sparse_layout: postings_out must be 8-byte aligned");
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.first()) {
         B200RET_CUDA_CHECK(cudaFuncSetAttribute(posting_layout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-        attr_set = true;
     }
     // Two launches: the shared memory of a warp is sized for the longest slice it may meet, and almost all slices are
     // short — sizing every warp for block_docs postings left 4 warps per SM and made the layout latency-bound (0.3 s).

@@ -385,11 +385,10 @@ extern "C" int b200ret_dense_search(const void* corpus_bf16, const void* queries
     } else {
         map_d = map_q;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.first()) {
         B200RET_CUDA_CHECK(cudaFuncSetAttribute(dense_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 static_cast<int>(D_SMEM_BYTES)));
-        attr_set = true;
     }
     const int grid = (sm_count() / 2) * 2;   // whole pairs
 

@@ -104,11 +104,10 @@ extern "C" int b200ret_merge_topk(const float* in_scores, const int64_t* in_ids,
     if (n_queries == 0) return B200RET_OK;
     B200RET_REQUIRE(in_scores && in_ids && out_scores && out_ids && out_counts, "merge_topk: null pointer");
     const size_t smem = (static_cast<size_t>(n_shards) * k + next_pow2(k)) * sizeof(uint64_t);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.first()) {
         B200RET_CUDA_CHECK(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (MERGE_MAX_CANDIDATES + B200RET_MAX_K) * (int)sizeof(uint64_t)));
-        attr_set = true;
     }
     merge_topk_kernel<<<n_queries, MERGE_THREADS, smem, stream>>>(in_scores, in_ids, n_shards, n_queries, k, out_scores,
                                                                   out_ids, out_counts);

@@ -519,11 +519,10 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
 static int block_docs_of_shape() { return BLOCK_DOCS; }
 
 static int launch_score(const ScoreParams& sp, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.first()) {
         B200RET_CUDA_CHECK(cudaFuncSetAttribute(sparse_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 static_cast<int>(SCORE_SMEM)));
-        attr_set = true;
     }
     // The item counter is 32 bits wide (claims run past the end by a few per warp): cut the block range so that one
     // launch hands out < 2^31 (query, block) items.
