@@ -31,7 +31,10 @@ constexpr int D_THREADS = 256;
 constexpr int D_TMEM_COLS = 512;           // 2 accumulator stages x 256 fp32 columns
 constexpr uint32_t D_TILE_BYTES = 128 * D_BLOCK_K * 2;            // one 128-row operand tile: 16 KB
 constexpr uint32_t D_STAGE_BYTES = 2 * D_TILE_BYTES;              // A half + B half per CTA
-constexpr int D_ROUND0_DOCS = 8192;        // first round / safe-schedule round size (candidate capacity = k + this)
+#ifndef B200RET_DENSE_ROUND0_DOCS
+#define B200RET_DENSE_ROUND0_DOCS 8192
+#endif
+constexpr int D_ROUND0_DOCS = B200RET_DENSE_ROUND0_DOCS;        // first round / safe-schedule round size (candidate capacity = k + this)
 constexpr int D_UNIT_DOCS = D_BLOCK_N;     // round unit = one doc tile
 #ifndef B200RET_DENSE_TILES_PER_PAIR
 #define B200RET_DENSE_TILES_PER_PAIR 256
