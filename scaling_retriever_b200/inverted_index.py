@@ -109,13 +109,7 @@ class IndexDictOfArray:
         return all(os.path.exists(p) for p in self._csr_paths()) or os.path.exists(self.filename)
 
     def _load(self, dim_voc):
-        if all(os.path.exists(p) for p in self._csr_paths()):
-            off, ids, w = (np.load(p) for p in self._csr_paths())
-            if dim_voc is not None and dim_voc != len(off) - 1:   # the reference trusts dim_voc (inverted_index.py:25-26)
-                off = _resize_offsets(off, dim_voc)
-        else:
-            off, ids, w = _load_hdf5(self.filename, dim_voc)
-        self._set_csr_host(off.astype(np.int64), ids.astype(np.int32), w.astype(np.float32))
+        self._set_csr_host(*read_index_dir(self.index_path, os.path.basename(self.filename), dim_voc))
         self._all_keys = True
 
     def _set_csr_host(self, off, ids, w):
@@ -286,16 +280,32 @@ def _load_hdf5(filename, dim_voc):
     return off, ids, vals
 
 
+def read_index_dir(index_path, filename="array_index.h5py", dim_voc=None):
+    """Posting lists of an index directory as host CSR arrays (term_offsets int64[V+1], doc_ids int32, weights fp32): the
+    native csr_*.npy bundle when present, else the reference's HDF5 file (needs h5py).  No doc_ids.pkl involved."""
+    paths = [os.path.join(index_path, f) for f in CSR_FILES]
+    if all(os.path.exists(p) for p in paths):
+        off, ids, w = (np.load(p) for p in paths)
+        if dim_voc is not None and dim_voc != len(off) - 1:   # the reference trusts dim_voc (inverted_index.py:25-26)
+            off = _resize_offsets(off, dim_voc)
+    else:
+        off, ids, w = _load_hdf5(os.path.join(index_path, filename), dim_voc)
+    return off.astype(np.int64), ids.astype(np.int32), w.astype(np.float32)
+
+
 def merge_indexes(model_name_or_path, filename="array_index.h5py", index_name="index", index_dir=None):
     """Merge per-rank index dirs `index_0`, `index_1`, ... into `index` (reference inverted_index.py:108-170):
-    per term, the posting arrays of the shards are appended in directory order; doc_ids maps are unioned;
-    L0_d is averaged.  Here the append is one stable GPU sort of the concatenated shard postings by term."""
+    per term, the posting arrays of the shards are appended in directory order; doc_ids maps are unioned; L0_d is
+    averaged; index_dist.json is dict.update()d shard after shard exactly like the reference (:149-150), i.e. a term's
+    entry is its count in the LAST shard that holds it, not the sum.  Here the append is one stable GPU sort of the concatenated shard postings by term."""
     with open(os.path.join(model_name_or_path, "config.json")) as fin:
         config = json.load(fin)
     dim_voc = config["vocab_size"]
     print("dim_voc: ", dim_voc)
     root = index_dir if index_dir is not None else model_name_or_path
-    index_dirs = [os.path.join(root, d) for d in os.listdir(root) if d.startswith(index_name)]
+    # the reference takes os.listdir order as it comes (the order of the shards inside a posting list follows it);
+    # sorted here so that the merged index is deterministic: index_0, index_1, ...
+    index_dirs = [os.path.join(root, d) for d in sorted(os.listdir(root)) if d.startswith(index_name) and d != index_name]
     assert len(index_dirs) in [1, 2, 4], index_dirs
     if len(index_dirs) == 1:
         print("only one index, no need to merge")
@@ -303,8 +313,8 @@ def merge_indexes(model_name_or_path, filename="array_index.h5py", index_name="i
     rows, cols, vals = [], [], []
     doc_ids, index_dist, index_stats = dict(), {}, {"L0_d": 0}
     for idx_dir in index_dirs:
-        shard = IndexDictOfArray(idx_dir, filename=filename, dim_voc=dim_voc)
-        off, ids, w = shard.csr_host()
+        off, ids, w = read_index_dir(idx_dir, filename, dim_voc)   # like the reference: the posting file only (a shard's
+        #                                                             doc_ids.pkl need not start at row 0)
         cols.append(np.repeat(np.arange(dim_voc, dtype=np.int32), np.diff(off)))
         rows.append(ids)
         vals.append(w)

@@ -245,3 +245,64 @@ def test_hybrid_index_then_retrieve_equals_the_two_single_paths(golden, cuda, tm
     top_ids, top_scores = dense_index.search_knn(dense_q.numpy(), topk)
     for qid, docids, scores in zip(qids, top_ids, top_scores):
         assert dense_res[qid] == {str(a): float(b) for a, b in zip(docids, scores)}
+
+
+def test_merge_indexes_matches_reference_golden(golden, cuda, tmp_path):
+    """utils/inverted_index.py:108-170: per-rank dirs index_0 / index_1 (rows interleaved g_row = row * W + rank) are merged
+    into `index`: golden case B is the reference's own merge of the same two shards (rank 0's postings, then rank 1's)."""
+    from scaling_retriever.utils.inverted_index import merge_indexes
+    row, col, val = golden["B_row"], golden["B_col"], golden["B_val"]
+    n_terms, n_docs = int(golden["B_n_terms"]), int(golden["B_n_docs"])
+    root = tmp_path / "model"
+    root.mkdir()
+    with open(root / "config.json", "w") as f:
+        json.dump({"vocab_size": n_terms}, f)
+    for r in range(2):
+        m = row % 2 == r
+        d = root / f"index_{r}"
+        shard_index = IndexDictOfArray(str(d), force_new=True, dim_voc=n_terms)
+        shard_index.add_batch_document(row[m], col[m], val[m], n_docs=int(len(np.unique(row[m]))))
+        shard_index.save()
+        with open(d / "doc_ids.pkl", "wb") as f:
+            pickle.dump({int(x): f"D{int(x)}" for x in np.unique(row[m])}, f)
+        with open(d / "index_stats.json", "w") as f:
+            json.dump({"L0_d": 10.0 + r}, f)
+    merge_indexes(str(root))
+    merged = IndexDictOfArray(str(root / "index"), dim_voc=n_terms)
+    off, ids, vals = golden["B_offsets"], golden["B_ids"], golden["B_vals"]
+    for t in range(n_terms):
+        assert np.array_equal(merged.index_doc_id[t], ids[off[t]:off[t + 1]]), t
+        assert np.array_equal(merged.index_doc_value[t].view(np.uint32), vals[off[t]:off[t + 1]].view(np.uint32)), t
+    assert len(pickle.load(open(root / "index" / "doc_ids.pkl", "rb"))) == len(np.unique(row))
+    with open(root / "index" / "index_stats.json") as f:
+        assert abs(json.load(f)["L0_d"] - 10.5) < 1e-9
+    with open(root / "index" / "index_dist.json") as f:
+        dist = json.load(f)
+    # reference quirk kept (inverted_index.py:149-150): dict.update per shard -> the count of the LAST shard holding the term
+    expect = {}
+    for r in range(2):
+        m = row % 2 == r
+        expect.update({str(int(t)): int(c) for t, c in zip(*np.unique(col[m], return_counts=True))})
+    assert dist == expect
+
+
+def test_dense_indexer_serialize_roundtrip(cuda, tmp_path):
+    """DenseIndexer.serialize / get_files / index_exists / deserialize (indexer.py:145-184): index.dpr + index_meta.dpr."""
+    n, d, k = 700, 64, 20
+    g = torch.Generator().manual_seed(5)
+    docs = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=1).numpy()
+    queries = torch.nn.functional.normalize(torch.randn(9, d, generator=g), dim=1).numpy()
+    ids = [f"P{3 * i}" for i in range(n)]
+    index = DenseFlatIndexer()
+    index.init_index(d)
+    index.index_data(docs, ids)
+    path = str(tmp_path)
+    assert not index.index_exists(path)
+    index.serialize(path)
+    assert index.index_exists(path) and [os.path.basename(f) for f in index.get_files(path)] == ["index.dpr", "index_meta.dpr"]
+    loaded = DenseFlatIndexer()
+    loaded.init_index(d)
+    loaded.deserialize(path)
+    a_ids, a_scores = index.search_knn(queries, k)
+    b_ids, b_scores = loaded.search_knn(queries, k)
+    assert a_ids == b_ids and np.array_equal(a_scores, b_scores)
