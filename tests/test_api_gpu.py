@@ -284,6 +284,17 @@ def test_merge_indexes_matches_reference_golden(golden, cuda, tmp_path):
         m = row % 2 == r
         expect.update({str(int(t)): int(c) for t, c in zip(*np.unique(col[m], return_counts=True))})
     assert dist == expect
+    # the merged lists are not doc-sorted (rank 0's rows, then rank 1's): the retriever re-sorts them on the GPU when it moves
+    # the index to HBM, and scores must equal the oracle's over the merged lists
+    retriever = SparseRetrieval(torch.nn.Linear(1, 1), {"index_dir": str(root / "index"), "out_dir": str(tmp_path)}, n_terms, 0)
+    index_ids, index_vals = sparse_oracle.csr_to_dicts(off, ids, vals, n_terms)
+    rng = np.random.default_rng(1)
+    for _ in range(4):
+        q_t = np.sort(rng.choice(n_terms, size=12, replace=False)).astype(np.int32)
+        q_w = rng.random(12, dtype=np.float32) + 0.1
+        f, neg = retriever.score_float(q_t, q_w, threshold=0.0)
+        o_f, o_neg = sparse_oracle.score_float(index_ids, index_vals, q_t, q_w, 0.0, n_docs)
+        assert np.array_equal(f, o_f) and np.array_equal(neg.view(np.uint32), o_neg.view(np.uint32))
 
 
 def test_dense_indexer_serialize_roundtrip(cuda, tmp_path):
