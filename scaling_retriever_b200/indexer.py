@@ -236,14 +236,19 @@ class DenseFlatIndexer(DenseIndexer):
         self.index = corpus
         logger.info("total data indexed %d", n_total)
 
-    def search_arrays(self, query_reps, top_docs):
-        """(scores fp32 [Q, k] descending, row labels int64 [Q, k], -1 padded) as host numpy arrays."""
+    def search_arrays(self, query_reps, top_docs, host_ranks="all"):
+        """(scores fp32 [Q, k] descending, row labels int64 [Q, k], -1 padded) as host numpy arrays.
+        `host_ranks="first"` (sharded search only): the merged result is copied to the host of the first worker alone — the
+        rank that writes the run file — and the other ranks return (None, None)."""
         with torch.cuda.device(self.device):
             q = _stage_in(self._staging, self.device, "queries", query_reps, torch.float32)   # pinned -> device
             q16 = ops.f32_to_bf16(q)
             scores, ids, _ = ops.dense_search(self.index, q16, int(top_docs), doc_id_base=self._row_lo)
             if _world_size() > 1:
                 scores, ids, _ = shard.merge_shards(scores, ids, int(top_docs))
+            if host_ranks == "first" and not is_first_worker():
+                torch.cuda.current_stream().synchronize()
+                return None, None
             out_s, out_i = _stage_out(self._staging, "scores", scores), _stage_out(self._staging, "ids", ids)
             torch.cuda.current_stream().synchronize()
             return out_s.numpy(), out_i.numpy()
@@ -432,9 +437,11 @@ class SparseRetrieval:
         return sparse_query_vecs, qids
 
     # ---- the hot path -----------------------------------------------------------------------------------------
-    def search_arrays(self, q_offsets, q_terms, q_weights, topk, threshold=0.0):
+    def search_arrays(self, q_offsets, q_terms, q_weights, topk, threshold=0.0, host_ranks="all"):
         """HOST query arrays -> HOST result arrays (scores fp32 [Q,k], row ids int64 [Q,k], counts int32 [Q]).
-        Copies through pinned memory; this is the call bench.py times end to end."""
+        Copies through pinned memory; this is the call bench.py times end to end.  `host_ranks="first"` (sharded search
+        only): the merged result goes to the host of the first worker alone — the rank that writes run.json — and the
+        other ranks return (None, None, None)."""
         dev = self._cuda
         with torch.cuda.device(dev):
             d_off = self._stage_in("q_off", q_offsets, torch.int32)
@@ -444,6 +451,9 @@ class SparseRetrieval:
                                                     doc_id_base=self.doc_id_base)
             if self.shard_plan.world_size > 1:
                 scores, ids, counts = shard.merge_shards(scores, ids, int(topk))
+            if host_ranks == "first" and not is_first_worker():
+                torch.cuda.current_stream().synchronize()
+                return None, None, None
             out = [self._stage_out(name, t) for name, t in (("scores", scores), ("ids", ids), ("counts", counts))]
             torch.cuda.current_stream().synchronize()
             return tuple(o.numpy() for o in out)
