@@ -65,7 +65,8 @@ int b200ret_profile_read(int kind, double* total_ms, int64_t* timed_launches, in
  *   term t at [term_offsets[t], term_offsets[t+1]) in FEED order (stable) when sort_docs == 0, or in
  *   ascending doc-id order when sort_docs != 0 (what the search kernels need; identical to feed order
  *   for the single-rank row-major feed of SparseIndexer.index).
- * Implementation: hand-written stable LSD radix sort (match-any multisplit) + boundary scan.
+ * Implementation: hand-written stable LSD radix sort (9-bit digits, ballot multisplit per warp, every 8192-posting
+ * tile staged in digit order in shared memory and written out as contiguous runs) + boundary scan.
  * ---------------------------------------------------------------------------------------------- */
 size_t b200ret_csr_build_workspace_bytes(int64_t nnz, int32_t n_terms, int32_t n_docs, int sort_docs);
 
