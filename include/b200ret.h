@@ -168,6 +168,26 @@ int b200ret_merge_topk(const float* in_scores, const int64_t* in_ids, int32_t n_
                        int32_t n_queries, int32_t k,
                        float* out_scores, int64_t* out_ids, int32_t* out_counts, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (5) Result materialisation (HOST pointers only, no device work): write run.json
+ * {qid: {external doc id: score}} straight from the [n_queries, row_stride] result arrays.
+ * Replaces `res[str(qid)][str(doc_ids[id_])] = float(sc)` (scaling_retriever/indexer.py:429-430; the same
+ * loop in eval_dense.py:229-241) followed by json.dump(res) (indexer.py:537-538): byte-identical output for
+ * distinct query ids and distinct external ids inside a row (callers check), formatted in parallel.
+ *   ids/scores: row q holds counts[q] live entries (counts NULL = row_stride everywhere); a query with
+ *   count 0 gets NO key (the reference's defaultdict never sees it).
+ *   qid_blob/qid_offsets[n_queries+1]: UTF-8 text of str(qid) per query, every entry followed by one NUL byte
+ *   (entry q = qid_blob[qid_offsets[q] .. qid_offsets[q+1] - 1)).
+ *   external ids of row label r: docid_blob[docid_offsets[r] .. docid_offsets[r+1] - 1) (same layout), or
+ *   str(docid_ints[r]) when the integer table is given instead, or str(r) when both are NULL.
+ *   Negative labels index from the end of the table like the reference's Python list (indexer.py:212).
+ * ---------------------------------------------------------------------------------------------- */
+int b200ret_write_run_json(const char* path_host, const int64_t* ids_host, const float* scores_host,
+                           const int32_t* counts_host, int32_t n_queries, int32_t row_stride,
+                           const char* qid_blob_host, const int64_t* qid_offsets_host,
+                           const char* docid_blob_host, const int64_t* docid_offsets_host,
+                           const int64_t* docid_ints_host, int64_t n_doc_ids, int64_t* bytes_written_host);
+
 #ifdef __cplusplus
 }
 #endif

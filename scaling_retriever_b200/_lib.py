@@ -41,6 +41,8 @@ PROTOTYPES = {
                                       _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_sz, _c_ptr]),
     "b200ret_f32_to_bf16": (_c_int, [_c_ptr, _c_ptr, _c_i64, _c_ptr]),
     "b200ret_merge_topk": (_c_int, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_ptr, _c_ptr]),
+    "b200ret_write_run_json": (_c_int, [ctypes.c_char_p, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr,
+                                        _c_ptr, _c_ptr, _c_ptr, _c_i64, ctypes.POINTER(_c_i64)]),
 }
 
 ERROR_NAMES = {-1: "EINVAL", -2: "ECUDA", -3: "EWORKSPACE", -4: "EUNSORTED", -5: "EOVERFLOW"}

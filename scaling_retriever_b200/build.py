@@ -19,6 +19,7 @@ STAMP_PATH = os.path.join(PKG_DIR, ".libb200ret.stamp")
 NVCC_FLAGS = [
     "-shared", "-Xcompiler", "-fPIC", "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
+    "-Xcompiler", "-fopenmp",      # host-side result writer (csrc/run_writer.cpp) formats queries in parallel
 ]
 
 
@@ -30,7 +31,7 @@ def _nvcc():
 
 
 def _sources():
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cpp")))
 
 
 def _digest():

@@ -24,6 +24,7 @@ from tqdm import tqdm
 
 from . import ops, shard
 from .inverted_index import IndexDictOfArray
+from .results import ExternalIds, LazyRun
 from .utils import is_first_worker, obtain_doc_vec_dir_files, rank as _rank, supports_bfloat16, to_list, world_size as _world_size
 
 logger = logging.getLogger()
@@ -211,6 +212,7 @@ class DenseFlatIndexer(DenseIndexer):
         self.hidden_dim = None
         self._row_lo = 0
         self._staging = {}
+        self._ext = None
 
     def init_index(self, hidden_dim):
         self.device = _cuda_device(self.device)
@@ -255,10 +257,15 @@ class DenseFlatIndexer(DenseIndexer):
 
     def search_knn(self, query_reps: np.array, top_docs: int):
         scores, indexes = self.search_arrays(query_reps, top_docs)
-        # reference indexer.py:212 (a -1 label indexes the last id there; kept identical)
-        id_arr = self.index_id_to_db_id
-        top_doc_ids = [[id_arr[idx] for idx in per_query_indexes] for per_query_indexes in indexes.tolist()]
+        # reference indexer.py:212: [[index_id_to_db_id[idx] ...]] (a -1 label indexes the last id there; kept identical),
+        # as one object-array gather instead of Q*k Python list lookups
+        top_doc_ids = self.external_ids().obj[indexes].tolist()
         return top_doc_ids, scores.copy()   # search_arrays returns views of reusable pinned staging buffers
+
+    def external_ids(self):
+        if self._ext is None or self._ext.size != len(self.index_id_to_db_id):
+            self._ext = ExternalIds(self.index_id_to_db_id)
+        return self._ext
 
     def get_index_name(self):
         return "flat_index"
@@ -499,29 +506,22 @@ class SparseRetrieval:
 
     def _external_ids(self):
         if self._ext_ids is None:
-            ext = np.empty(self.size_collection, dtype=object)
-            if isinstance(self.doc_ids, dict):
-                for k, v in self.doc_ids.items():
-                    ext[k] = v
-            else:
-                ext[:len(self.doc_ids)] = list(self.doc_ids)
-            self._ext_ids = ext
+            self._ext_ids = ExternalIds(self.doc_ids, self.size_collection)
         return self._ext_ids
 
     def _sparse_retrieve_multithreaded(self, sparse_query_vecs, qids, threshold=0., topk=1000):
         """Same contract as the reference (indexer.py:405-474): returns (res, stats) with
         res[str(qid)][str(doc_ids[row])] = float(score); queries without an eligible doc get no key.  The 4-thread
-        numba loop is replaced by one batched GPU search over all queries."""
+        numba loop is replaced by one batched GPU search over all queries, and `res` is a read-only Mapping over the
+        result arrays (results.LazyRun: inner dicts are built on access, `.to_dict()` gives the eager dict of dicts) —
+        the reference spends ~5 s in its per-pair insert loop at 6,980 x 1000 pairs (:429-430)."""
         q_offsets, q_terms, q_weights = pack_queries(sparse_query_vecs)
         scores, ids, counts = self.search_arrays(q_offsets, q_terms, q_weights, topk, threshold)
-        ext = self._external_ids()
-        res = defaultdict(dict)
+        # search_arrays hands out views of reusable pinned staging buffers: the run owns copies
+        res = LazyRun(qids, np.array(ids), np.array(scores), np.array(counts), self._external_ids())
         stats = defaultdict(float)
-        for i, qid in enumerate(qids):
-            c = int(counts[i])
-            if c:
-                res[str(qid)].update(zip(map(str, ext[ids[i, :c]].tolist()), scores[i, :c].astype(float).tolist()))
-            stats["L0_q"] += (q_offsets[i + 1] - q_offsets[i]) / len(qids)
+        for n in np.diff(q_offsets).tolist():
+            stats["L0_q"] += n / len(qids)
         return res, stats
 
     def retrieve(self, q_loader, topk, threshold=0.):
@@ -531,9 +531,17 @@ class SparseRetrieval:
             if self.compute_stats:
                 with open(os.path.join(self.out_dir, "q_stats.json"), "w") as handler:
                     json.dump(stats, handler)
-            with open(os.path.join(self.out_dir, "run.json"), "w") as handler:
-                handler.write(json.dumps(res))   # one-shot C encoder: same bytes as json.dump, half the time at Q*k = 7 M pairs
+            _write_run(res, os.path.join(self.out_dir, "run.json"))   # native formatter: same bytes as json.dump(res)
         return res
+
+
+def _write_run(res, path):
+    """run.json (reference indexer.py:537-538): formatted from the result arrays when `res` is a LazyRun."""
+    if isinstance(res, LazyRun):
+        return res.write_json(path)
+    with open(path, "w") as handler:
+        handler.write(json.dumps(res))
+    return "python"
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -676,12 +684,11 @@ class HybridRetriever:
         print("finished indexing")
 
     def _dense_retrieve(self, query_reps, qids, topk=1000):
-        res = defaultdict(dict)
-        top_doc_ids, top_scores = self.dense_index.search_knn(query_reps, topk)
+        """reference indexer.py:973-982; the run is a LazyRun over the [Q, k] arrays (rows padded with label -1 map to the
+        last id like the reference's list indexing, :212)."""
         assert len(qids) == len(query_reps), (len(qids), len(query_reps))
-        for qid, docids, scores in zip(qids, top_doc_ids, top_scores.astype(float).tolist()):
-            res[str(qid)].update(zip(map(str, docids), scores))
-        return res
+        scores, indexes = self.dense_index.search_arrays(query_reps, topk)
+        return LazyRun(qids, np.array(indexes), np.array(scores), None, self.dense_index.external_ids())
 
     def _sparse_retrieve(self, sparse_query_vecs, qids, threshold=0., topk=1000):
         return self.sparse._sparse_retrieve_multithreaded(sparse_query_vecs, qids, threshold=threshold, topk=topk)
@@ -695,8 +702,6 @@ class HybridRetriever:
         if is_first_worker():
             with open(os.path.join(self.sparse_out_dir, "q_stats.json"), "w") as handler:
                 json.dump(sparse_stats, handler)
-            with open(os.path.join(self.sparse_out_dir, "run.json"), "w") as handler:
-                handler.write(json.dumps(sparse_res))
-            with open(os.path.join(self.dense_out_dir, "run.json"), "w") as handler:
-                handler.write(json.dumps(dense_res))
+            _write_run(sparse_res, os.path.join(self.sparse_out_dir, "run.json"))
+            _write_run(dense_res, os.path.join(self.dense_out_dir, "run.json"))
         return sparse_res, dense_res

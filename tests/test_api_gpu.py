@@ -115,7 +115,7 @@ def test_sparse_index_then_retrieve_matches_reference_run(golden, golden_run, cu
         full[str(qid)] = sc
     check_run(res, golden_run["res"], full, lambda d: int(d[1:]) // 7)
     with open(os.path.join(out_dir, "run.json")) as f:
-        assert json.load(f) == json.loads(json.dumps(res))
+        assert f.read() == json.dumps(res.to_dict())     # native writer: the bytes json.dump(res) would have written
     with open(os.path.join(out_dir, "q_stats.json")) as f:
         assert abs(json.load(f)["L0_q"] - golden_run["stats"]["L0_q"]) < 1e-9
 
@@ -233,7 +233,7 @@ def test_hybrid_index_then_retrieve_equals_the_two_single_paths(golden, cuda, tm
     for sub in ("sparse/run.json", "sparse/q_stats.json", "dense/run.json"):
         assert os.path.exists(os.path.join(out_dir, sub)), sub
     with open(os.path.join(out_dir, "dense", "run.json")) as f:
-        assert json.load(f) == json.loads(json.dumps(dense_res))
+        assert f.read() == json.dumps(dense_res.to_dict())
 
     single_out = str(tmp_path / "single")
     os.makedirs(single_out)
