@@ -1,18 +1,35 @@
 #!/usr/bin/env python
 """Headline benchmark: top-1000 QPS of the retrieval hot path on synthetic MS-MARCO-shaped data (BASELINE.json).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload sparse|dense]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload both|sparse|dense] [--dim D]
 
 A "step" is one pass of the hot path over the whole query batch (6,980 queries, top-1000) against the index resident
-in HBM.  Default workload = BASELINE.json configs[1]: sparse inverted-index retrieval over 8,841,823 synthetic docs x
-128,256 terms; for N > 1 (torchrun, one rank per GPU) the corpus is sharded by doc-id range, every rank searches its
-shard and the per-shard top-k rows are merged after an NCCL all-gather ("strong" scaling: total work fixed).
-Rank 0 prints ONE JSON line.  Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max
-over ranks; the index (14 GB) is far larger than L2 (126 MB), so no explicit L2 flush is needed between steps.
-`--impl reference` times the CPU port of the reference's numba path (oracle/sparse_oracle.c, all host threads) on a
+in HBM.  The default run measures BOTH halves of the metric ("sparse & dense") and prints ONE JSON line on rank 0:
+
+  * top level = BASELINE.json configs[1]: sparse inverted-index retrieval over 8,841,823 synthetic docs x 128,256 terms;
+  * "dense"   = configs[2]: flat inner-product search over 8,841,823 x 2048 bf16 (tcgen05 GEMM + fused top-k), a complete
+    sub-record with its own value / ms_per_step / e2e / roofline / clocks / cpu_baseline;
+  * "dense_4096" = configs[3] (8,841,823 x 4096, corpus sharded over the GPUs) when N >= 8.
+
+For N > 1 (torchrun, one rank per GPU) the corpus is sharded by doc-id range, every rank searches its shard and the
+per-shard top-k rows are merged after an NCCL exchange of packed candidate keys ("strong" scaling: total work fixed).
+Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks; the index / corpus
+(GBs) is far larger than L2 (126 MB), so no explicit L2 flush is needed between steps.
+
+Per workload the line reports
+  value     device-resident QPS (inputs already in HBM),
+  e2e       the same search through the class-API call with HOST buffers (pinned h2d of the queries + d2h of the rows),
+  e2e_api   the REFERENCE-FACING method itself: SparseRetrieval._sparse_retrieve_multithreaded(query vecs, qids, ...) /
+            DenseFlatIndexer.search_knn(query_reps, k) — what eval_sparse.py / eval_dense.py call — wall clock, plus the
+            time retrieve() additionally spends writing run.json,
+  result_digest  sha256 over the merged ids + score bits: equal digests at N = 1/2/4/8 prove sharded == unsharded.
+
+`--impl reference` times the CPU port of the reference's path (sparse: oracle/sparse_oracle.c, the numba scorer +
+argpartition restated in C + OpenMP; dense: the fp32 IndexFlatIP restatement on torch/MKL) with ALL host cores on a
 bounded sample of the same workload; only that leg and the cpu_baseline leg execute anything under oracle/.
 """
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -21,11 +38,26 @@ import sys
 import tempfile
 import time
 
-import numpy as np
-import torch
-
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; the CPU legs (reference arm, cpu_baseline) must use the
+# box's cores, so thread counts are set explicitly from host_cores() and never read from the environment.
+HOST_CORES = host_cores()
+if os.environ.get("OMP_NUM_THREADS") == "1" and "LOCAL_RANK" in os.environ:
+    os.environ["OMP_NUM_THREADS"] = str(HOST_CORES)
+os.environ.setdefault("NUMBA_NUM_THREADS", str(HOST_CORES))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
 
 from scaling_retriever_b200 import synth  # noqa: E402
 
@@ -141,7 +173,9 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ----------------------------------------------------------------------------------------------------- workloads
+# ------------------------------------------------------------------------------------------------- workload descriptions
+# The `config` dicts are built from the command line only, so both arms (`--impl b200` / `--impl reference`) of the same
+# command print IDENTICAL dicts; everything measured goes elsewhere in the line.
 
 def sparse_sizes(args):
     n_docs = args.n_docs or synth.MSMARCO_DOCS
@@ -149,30 +183,113 @@ def sparse_sizes(args):
     return n_docs, n_queries, synth.LLAMA3_VOCAB
 
 
-def workload_name(args):
+def parallelism(n_gpus):
+    return (f"doc-range shards x{n_gpus}, packed-key all-to-all + per-slice merge + all-gather over NCCL; queries replicated"
+            if n_gpus > 1 else "1 GPU")
+
+
+L2_NOTE = "inputs larger than L2 (index / corpus of several GB vs 126 MB L2), no flush"
+
+
+def sparse_config(args):
     n_docs, n_queries, n_terms = sparse_sizes(args)
-    return (f"sparse inverted-index top-{K_TOP}, synthetic {n_docs:,} docs x {n_terms:,} terms (~200 nnz/doc), "
-            f"{n_queries:,} queries (~40 nnz) [BASELINE.json configs[1]]")
+    return {"workload": (f"sparse inverted-index top-{K_TOP}, synthetic {n_docs:,} docs x {n_terms:,} terms (~200 nnz/doc), "
+                         f"{n_queries:,} queries (~40 nnz) [BASELINE.json configs[1]]"),
+            "n_docs": n_docs, "n_queries": n_queries, "k": K_TOP, "n_terms": n_terms,
+            "parallelism": parallelism(args.gpus), "l2": L2_NOTE}
 
 
-def run_b200(args):
-    import torch.distributed as dist
+def dense_config(args, dim):
+    n_docs = args.n_docs or synth.MSMARCO_DOCS
+    n_queries = args.n_queries or synth.MSMARCO_DEV_QUERIES
+    cfg = "configs[2]" if dim == 2048 else ("configs[3]" if dim == 4096 else "configs[4] sweep point")
+    return {"workload": (f"dense flat inner-product top-{K_TOP}, synthetic {n_docs:,} x {dim} bf16 corpus (L2-normalised "
+                         f"Gaussian rows), {n_queries:,} queries [BASELINE.json {cfg}]"),
+            "n_docs": n_docs, "n_queries": n_queries, "k": K_TOP, "dim": dim,
+            "parallelism": parallelism(args.gpus), "l2": L2_NOTE}
+
+
+def dense_dims(args):
+    if args.workload == "sparse":
+        return []
+    if args.workload == "dense":
+        return [args.dim]
+    return [2048] + ([4096] if args.gpus >= 8 else [])
+
+
+def result_digest(scores, ids):
+    """sha256 over the merged rows (ids + fp32 score bits) — identical at every N iff sharded == unsharded."""
+    h = hashlib.sha256()
+    h.update(ids.cpu().numpy().tobytes())
+    h.update(scores.cpu().numpy().view(np.uint32).tobytes())
+    return h.hexdigest()
+
+
+class Ctx:
+    """Process-wide state of the GPU arm: rank / world / device, the process group, measured peaks."""
+
+    def __init__(self, args):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank, self.world, self.local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        assert self.world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={self.world} (launch N>1 with torchrun)"
+        self.peaks = load_peaks()
+
+    def barrier(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = torch.tensor([float(x)], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def time_device(self, step, steps):
+        """K steps between CUDA events, barrier + synchronize on both sides, max over ranks -> (ms per step, last output)."""
+        self.barrier()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        out = None
+        for _ in range(steps):
+            out = step()
+        end.record()
+        self.barrier()
+        return self.max_over_ranks(start.elapsed_time(end)) / steps, out
+
+    def time_wall(self, fn, steps, warmup=1):
+        """Host wall clock per call of `fn` (the end-to-end legs), barrier on both sides, max over ranks."""
+        out = None
+        for _ in range(warmup):
+            out = fn()
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = fn()
+        self.barrier()
+        return self.max_over_ranks((time.perf_counter() - t0) / steps), out
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------------- sparse (GPU)
+
+def bench_sparse(args, ctx):
     from scaling_retriever_b200 import ops, shard
     from scaling_retriever_b200.indexer import SparseRetrieval
-
-    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch N>1 with torchrun)"
-    peaks = load_peaks()
-
+    dev, rank, world = ctx.dev, ctx.rank, ctx.world
     n_docs, n_queries, n_terms = sparse_sizes(args)
-    plan = shard.ShardPlan(n_docs, world)
-    lo, hi = plan.bounds(rank)
+    lo, hi = shard.ShardPlan(n_docs, world).bounds(rank)
 
     # ---- synthetic corpus shard -> CSR index + skip table in HBM (build timed for information) --------------------
     t0 = time.perf_counter()
@@ -206,130 +323,118 @@ def run_b200(args):
     def step():
         s, i, c = ops.sparse_search(index, q_off, q_terms, q_w, K_TOP, 0.0, doc_id_base=lo)
         if world > 1:
-            s, i, c = shard.merge_shards(s, i, K_TOP)
+            s, i, c = shard.merge_shards(s, i, K_TOP, n_docs_total=n_docs)
         return s, i, c
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # nvidia-smi is started BEFORE the warm-up: attaching to the driver stalls the GPU for tens of ms, which must not land
-    # in the timed region; the samples it takes during warm-up + timed steps are all under the same load.
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    # The clock sampler is started BEFORE the warm-up: attaching to the driver stalls the GPU for tens of ms, which must not
+    # land in the timed region; the samples it takes during warm-up + timed steps are all under the same load.
+    sampler = ClockSampler(ctx.local_rank) if rank == 0 else None
     for _ in range(args.warmup):
         out = step()   # held like in the timed loop: the allocator's second set of output blocks is created here, not there
     ops.profile_read(ops.PROF_SPARSE_SCORE)     # drop warm-up records and launch counts
     ops.profile_read(ops.PROF_SPARSE_SELECT)
 
     # ---- device-resident throughput (`value`) ----------------------------------------------------------------
-    barrier()
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    marks = []
-    start.record()
-    for _ in range(args.steps):
-        out = step()
-        if os.environ.get("B200RET_BENCH_DEBUG"):
-            marks.append(torch.cuda.Event(enable_timing=True))
-            marks[-1].record()
-    end.record()
-    barrier()
-    if marks:
-        print("per-step ms:", [round(a.elapsed_time(b), 2) for a, b in zip([start] + marks[:-1], marks)], file=sys.stderr)
+    ms_per_step, out = ctx.time_device(step, args.steps)
     clocks = sampler.stop() if sampler else None
-    ms_total = torch.tensor([start.elapsed_time(end)], device=dev)
     score_ms, score_launches, all_launches = ops.profile_read(ops.PROF_SPARSE_SCORE)
     select_ms, _, _ = ops.profile_read(ops.PROF_SPARSE_SELECT)
     ops.profile_enable(False)
-    stats = torch.tensor([score_ms, float(algo_bytes), float(postings)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
-        gathered = [torch.zeros_like(stats) for _ in range(world)]
-        dist.all_gather(gathered, stats)
-    else:
-        gathered = [stats]
-    ms_per_step = float(ms_total.item()) / args.steps
     value = n_queries / (ms_per_step / 1e3)
 
-    # ---- end to end through the class API with HOST buffers (`e2e`) --------------------------------------------
-    retriever = SparseRetrieval.from_device_index(index, doc_id_base=lo, size_collection=n_docs)
+    # ---- end to end with HOST buffers (`e2e`): pinned h2d of the packed queries, search (+ merge), d2h of the rows --------
+    retriever = SparseRetrieval.from_device_index(index, doc_ids=range(n_docs), doc_id_base=lo, size_collection=n_docs)
     # N > 1: every rank copies its queries in and searches its shard; the merged result is read back by rank 0 (the rank that
     # writes run.json in retrieve()), host_ranks="first"
-    for _ in range(2):
-        retriever.search_arrays(h_off, h_terms, h_w, K_TOP, 0.0, host_ranks="first")
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e_scores, e_ids, e_counts = retriever.search_arrays(h_off, h_terms, h_w, K_TOP, 0.0, host_ranks="first")
-    barrier()
-    e2e_s = torch.tensor([(time.perf_counter() - t0) / args.steps], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s, e_out = ctx.time_wall(lambda: retriever.search_arrays(h_off, h_terms, h_w, K_TOP, 0.0, host_ranks="first"),
+                                 args.steps, warmup=2)
     h2d = h_off.nbytes + h_terms.nbytes + h_w.nbytes
     if rank == 0:
-        d2h = e_scores.nbytes + e_ids.nbytes + e_counts.nbytes
-        assert np.array_equal(e_ids, out[1].cpu().numpy())    # the host-buffer path returns the same rows
+        d2h = sum(x.nbytes for x in e_out)
+        assert np.array_equal(e_out[1], out[1].cpu().numpy())    # the host-buffer path returns the same rows
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    # ---- the reference-facing method (`e2e_api`): list of per-query (col, values) arrays + qids -> run mapping + stats ----
+    vecs = synth.queries_to_vecs(q_off, q_terms, q_w)
+    qids = list(range(n_queries))
+    api_steps = max(1, min(args.steps, 5))
+    api_s, api_out = ctx.time_wall(lambda: retriever._sparse_retrieve_multithreaded(vecs, qids, threshold=0.0, topk=K_TOP),
+                                   api_steps, warmup=1)
+    run_json = None
+    if rank == 0:
+        res, _ = api_out
+        assert len(res) == int((out[2] > 0).sum().item())
+        first = next(iter(res))
+        assert res[first][str(int(out[1][int(first), 0]))] == float(out[0][int(first), 0])
+        with tempfile.TemporaryDirectory() as tmp:
+            res.write_json(os.path.join(tmp, "warm.json"))                       # external-id table built once, like a retriever
+            t0 = time.perf_counter()
+            how = res.write_json(os.path.join(tmp, "run.json"))
+            write_s = time.perf_counter() - t0
+            run_json = {"writer": how, "seconds": write_s, "bytes": os.path.getsize(os.path.join(tmp, "run.json"))}
 
-    # roofline of the dominant kernel (sparse_score_kernel) on rank 0's shard: algorithmic bytes / CUDA-event time
-    r_score_ms, r_bytes, _ = gathered[0].tolist()
-    per_launch_ms = r_score_ms / max(score_launches, 1)
-    achieved = (r_bytes * args.steps) / (r_score_ms / 1e3) / 1e9 if r_score_ms > 0 else 0.0
-    traffic = None
-    prof = os.path.join(ROOT, "profiles", "sparse_score_traffic.json")
-    if os.path.exists(prof):
-        with open(prof) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "n_docs": n_docs, "n_queries": n_queries, "k": K_TOP, "n_terms": n_terms,
-                   "parallelism": (f"doc-range shards x{world} + NCCL all-gather merge; e2e: queries copied in on every rank, merged "
-                                   "result read back by rank 0") if world > 1 else "1 GPU",
-                   "l2": "inputs larger than L2 (index %.1f GB vs 126 MB L2), no flush" % (nnz * 8 / 1e9),
-                   "index_postings_this_rank": nnz, "postings_scored_per_query": postings / n_queries},
-        "e2e": {"value": n_queries / float(e2e_s.item()), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": int(all_launches),
-        "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "sparse_score_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                     "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks["source"],
-                     "launches": int(score_launches), "avg_launch_ms": per_launch_ms,
-                     "algorithmic_bytes_per_step": r_bytes, "score_kernel_share_of_step": (r_score_ms / args.steps) / ms_per_step,
-                     "select_kernels_ms_per_step": select_ms / args.steps,
-                     "note": "algorithmic bytes = 8 B per (query, term) posting as the reference streams them; the kernel "
-                             "re-serves postings shared between queries from L2, so achieved may exceed DRAM traffic"},
-        "build": {"csr_build_ms": build_ms, "radix_sort_ms": sort_ms, "skip_table_s": table_s, "synth_gen_s": gen_s,
-                  "postings": nnz, "algorithmic_gbs": nnz * 20 / (build_ms / 1e3) / 1e9},
-    }
-    if world == 1 and not args.no_cpu_baseline:
-        # the oracle gets the same posting lists the GPU searched (slices in bank order; order inside a list is irrelevant)
-        host = index.postings.cpu()
-        line["cpu_baseline"] = cpu_baseline(term_offsets, host[:, 0].contiguous(), host[:, 1].contiguous().view(torch.float32),
-                                            n_docs, h_off, h_terms, h_w, out)
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    digest = result_digest(out[0], out[1]) if rank == 0 else None
+    line = None
+    if rank == 0:
+        per_launch_ms = score_ms / max(score_launches, 1)
+        achieved = (algo_bytes * args.steps) / (score_ms / 1e3) / 1e9 if score_ms > 0 else 0.0
+        peak = ctx.peaks["hbm_gbs"]
+        build_gbs = nnz * 20 / (build_ms / 1e3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": sparse_config(args),
+            "e2e": {"value": n_queries / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "call": "SparseRetrieval.search_arrays(host CSR-packed queries) -> host rows (rank 0)"},
+            "e2e_api": {"value": n_queries / api_s, "unit": UNIT, "steps": api_steps,
+                        "call": "SparseRetrieval._sparse_retrieve_multithreaded(sparse_query_vecs, qids, threshold=0.0, topk=1000) "
+                                "[reference indexer.py:405-474] -> (lazy run mapping, stats)",
+                        "run_json": run_json,
+                        "with_run_json_value": n_queries / (api_s + run_json["seconds"]),
+                        "note": "with_run_json_value adds retrieve()'s run.json write (native formatter) to every call"},
+            "result_digest": digest,
+            "gpu_launches": int(all_launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "sparse_score_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": ctx.peaks["source"],
+                         "launches": int(score_launches), "avg_launch_ms": per_launch_ms,
+                         "algorithmic_bytes_per_step": algo_bytes, "score_kernel_share_of_step": (score_ms / args.steps) / ms_per_step,
+                         "select_kernels_ms_per_step": select_ms / args.steps,
+                         "note": "algorithmic bytes = 8 B per (query, term) posting as the reference streams them; the kernel "
+                                 "re-serves postings shared between queries from L2 (DRAM traffic ~ the index once per step: "
+                                 "profiles/, ncu), so the limiter is the L1/shared data pipe, not DRAM; traffic is not "
+                                 "measured inside bench.py"},
+            "build": {"kernel": "csr_build (radix sort)", "csr_build_ms": build_ms, "radix_sort_ms": sort_ms, "skip_table_s": table_s,
+                      "synth_gen_s": gen_s, "postings": nnz, "algorithmic_bytes": nnz * 20, "achieved": build_gbs, "unit": "GB/s",
+                      "peak": peak, "frac": build_gbs / peak},
+            "index_postings_this_rank": nnz, "postings_scored_per_query": postings / n_queries,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            # the oracle gets the same posting lists the GPU searched (slices in bank order; order inside a list is irrelevant)
+            host = index.postings.cpu()
+            h_ids, h_wts = host[:, 0].contiguous().numpy(), host[:, 1].contiguous().view(torch.float32).numpy()
+            h_toff = term_offsets.cpu().numpy()
+            del host
+            line["cpu_baseline"] = sparse_cpu_baseline(h_toff, h_ids, h_wts, n_docs, h_off, h_terms, h_w, out)
+            ref = reference_cpu_baseline(h_toff, h_ids, h_wts, n_docs, n_terms, h_off, h_terms, h_w, out)
+            if ref is not None:
+                line["cpu_baseline_reference"] = ref
+    del index, retriever, out
+    torch.cuda.empty_cache()
+    return line
 
 
-def cpu_baseline(term_offsets, doc_ids, weights, n_docs, h_off, h_terms, h_w, gpu_out, target_s=15.0):
+def sparse_cpu_baseline(off, ids, w, n_docs, h_off, h_terms, h_w, gpu_out, target_s=12.0):
     """The oracle port (C + OpenMP restatement of numba_score_float + select_topk) on this box's host cores, on a bounded
     query sample of the same index; also cross-checks the GPU rows of the sampled queries (ids + scores identical)."""
     from oracle import c_oracle
-    off, ids, w = term_offsets.cpu().numpy(), doc_ids.cpu().numpy(), weights.cpu().numpy()
-    threads = c_oracle.max_threads()
+    threads = HOST_CORES
     probe = min(len(h_off) - 1, threads)
     t0 = time.perf_counter()
-    c_oracle.sparse_search(off, ids, w, n_docs, h_off[:probe + 1], h_terms, h_w, K_TOP)
+    c_oracle.sparse_search(off, ids, w, n_docs, h_off[:probe + 1], h_terms, h_w, K_TOP, n_threads=threads)
     per_round = max(time.perf_counter() - t0, 1e-3)
     sample = int(min(len(h_off) - 1, max(probe, probe * round(target_s / per_round))))
     t0 = time.perf_counter()
-    o_scores, o_ids, o_counts = c_oracle.sparse_search(off, ids, w, n_docs, h_off[:sample + 1], h_terms, h_w, K_TOP)
+    o_scores, o_ids, o_counts = c_oracle.sparse_search(off, ids, w, n_docs, h_off[:sample + 1], h_terms, h_w, K_TOP, n_threads=threads)
     dt = time.perf_counter() - t0
     match = bool(np.array_equal(o_ids, gpu_out[1][:sample].cpu().numpy()) and
                  np.array_equal(o_scores.view(np.uint32), gpu_out[0][:sample].cpu().numpy().view(np.uint32)))
@@ -338,30 +443,55 @@ def cpu_baseline(term_offsets, doc_ids, weights, n_docs, h_off, h_terms, h_w, gp
                       f"oracle/sparse_oracle.c with {threads} OpenMP threads", "gpu_rows_identical": match}
 
 
-def dense_workload_name(n_docs, n_queries, dim):
-    cfg = "configs[2]" if dim == 2048 else ("configs[3]" if dim == 4096 else "configs[4] sweep point")
-    return (f"dense flat inner-product top-{K_TOP}, synthetic {n_docs:,} x {dim} bf16 corpus (L2-normalised Gaussian rows), "
-            f"{n_queries:,} queries [BASELINE.json {cfg}]")
+def reference_cpu_baseline(off, ids, w, n_docs, n_terms, h_off, h_terms, h_w, gpu_out, target_s=12.0, max_queries=200):
+    """The REFERENCE'S OWN code (SparseRetrieval._sparse_retrieve_multithreaded: 4 Python threads x numba prange,
+    indexer.py:405-474), unmodified, from the run-time copy under baseline/_ref/ (made by __graft_entry__.build() in the build
+    container; git-ignored), on a bounded query sample of the same index.  None when the copy or numba is absent."""
+    try:
+        from oracle import ref_runner
+        runner = ref_runner.load(os.path.join(ROOT, "baseline", "_ref"), threads=HOST_CORES)
+    except Exception as exc:   # copy absent / numba missing: the port above stands alone
+        return {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+    try:
+        retr = runner.make_retriever(off, ids, w, n_docs, n_terms)
+        vecs = [(h_terms[h_off[i]:h_off[i + 1]], h_w[h_off[i]:h_off[i + 1]]) for i in range(min(len(h_off) - 1, max_queries))]
+        t0 = time.perf_counter()
+        runner.retrieve(retr, vecs[:8], list(range(8)), K_TOP)          # JIT + first touch
+        warm_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        runner.retrieve(retr, vecs[:8], list(range(8)), K_TOP)
+        per8 = max(time.perf_counter() - t0, 1e-3)
+        sample = int(min(len(vecs), max(8, 8 * round(target_s / per8))))
+        t0 = time.perf_counter()
+        res, _ = runner.retrieve(retr, vecs[:sample], list(range(sample)), K_TOP)
+        dt = time.perf_counter() - t0
+        # cross-check: the reference's own result for a sampled query == the GPU row (same doc set, same scores)
+        g_ids, g_scores = gpu_out[1][:sample].cpu().numpy(), gpu_out[0][:sample].cpu().numpy()
+        same = True
+        for qi in (0, sample - 1):
+            ours = {str(int(d)): float(s) for d, s in zip(g_ids[qi], g_scores[qi]) if d >= 0}
+            theirs = res.get(str(qi), {})
+            kth = min(ours.values()) if ours else 0.0
+            same = same and {d for d, s in ours.items() if s > kth} == {d for d, s in theirs.items() if s > kth} \
+                and all(theirs[d] == s for d, s in ours.items() if d in theirs)
+        return {"value": sample / dt, "unit": UNIT, "cores": HOST_CORES, "kind": "reference",
+                "sample": f"first {sample} of the {len(h_off) - 1} queries over the full index in {dt:.1f} s through the reference's "
+                          f"own SparseRetrieval._sparse_retrieve_multithreaded (4 threads x numba prange, "
+                          f"{runner.numba_threads()} numba threads; index dicts are views of the same CSR; warm-up {warm_s:.1f} s)",
+                "gpu_rows_agree": bool(same)}
+    except Exception as exc:
+        return {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
 
 
-def run_b200_dense(args):
+# ------------------------------------------------------------------------------------------------------------ dense (GPU)
+
+def bench_dense(args, ctx, dim):
     """Dense workload (BASELINE.json configs[2]/[3]): bf16 tcgen05 GEMM + fused top-k over a doc-range shard per GPU."""
-    import torch.distributed as dist
     from scaling_retriever_b200 import ops, shard
     from scaling_retriever_b200.indexer import DenseFlatIndexer
-
-    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch N>1 with torchrun)"
-    peaks = load_peaks()
+    dev, rank, world = ctx.dev, ctx.rank, ctx.world
     n_docs = args.n_docs or synth.MSMARCO_DOCS
     n_queries = args.n_queries or synth.MSMARCO_DEV_QUERIES
-    dim = args.dim
     lo, hi = shard.ShardPlan(n_docs, world).bounds(rank)
     corpus = synth.gen_dense(n_docs, dim, seed=1234, device=dev, dtype=torch.bfloat16, row_lo=lo, row_hi=hi)
     q32 = synth.gen_dense(n_queries, dim, seed=4321, device=dev)
@@ -372,111 +502,112 @@ def run_b200_dense(args):
     def step():
         s, i, c = ops.dense_search(corpus, q16, K_TOP, doc_id_base=lo)
         if world > 1:
-            s, i, c = shard.merge_shards(s, i, K_TOP)
+            s, i, c = shard.merge_shards(s, i, K_TOP, n_docs_total=n_docs)
         return s, i, c
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     ops.profile_enable(True)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(ctx.local_rank) if rank == 0 else None
     for _ in range(args.warmup):
-        out = step()   # held like in the timed loop (see run_b200)
+        out = step()   # held like in the timed loop (see bench_sparse)
     ops.profile_read(ops.PROF_DENSE_GEMM)
     ops.profile_read(ops.PROF_SPARSE_SELECT)
-    barrier()
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    start.record()
-    for _ in range(args.steps):
-        out = step()
-    end.record()
-    barrier()
+    ms_per_step, out = ctx.time_device(step, args.steps)
     clocks = sampler.stop() if sampler else None
-    ms_total = torch.tensor([start.elapsed_time(end)], device=dev)
     gemm_ms, gemm_launches, all_launches = ops.profile_read(ops.PROF_DENSE_GEMM)
     select_ms, _, _ = ops.profile_read(ops.PROF_SPARSE_SELECT)
     ops.profile_enable(False)
-    if world > 1:
-        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
-    ms_per_step = float(ms_total.item()) / args.steps
     value = n_queries / (ms_per_step / 1e3)
 
-    # end to end through the class API: host fp32 queries -> pinned -> device cast -> search (-> merge) -> host rows
+    # end to end with HOST buffers: host fp32 queries -> pinned -> device cast -> search (-> merge) -> host rows (rank 0)
     index = DenseFlatIndexer(device=dev)
     index.init_index(dim)
-    index.index = corpus
-    index._row_lo = lo
-    for _ in range(2):
-        index.search_arrays(h_q, K_TOP, host_ranks="first")
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e_scores, e_ids = index.search_arrays(h_q, K_TOP, host_ranks="first")   # N > 1: result read back by rank 0
-    barrier()
-    e2e_s = torch.tensor([(time.perf_counter() - t0) / args.steps], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    index.index, index._row_lo, index._n_total = corpus, lo, n_docs
+    index.index_id_to_db_id = range(n_docs)
+    e2e_s, e_out = ctx.time_wall(lambda: index.search_arrays(h_q, K_TOP, host_ranks="first"), args.steps, warmup=2)
     if rank == 0:
-        assert np.array_equal(e_ids, out[1].cpu().numpy())
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    achieved = flops * args.steps / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": dense_workload_name(n_docs, n_queries, dim), "n_docs": n_docs, "n_queries": n_queries, "k": K_TOP,
-                   "dim": dim, "parallelism": (f"doc-range shards x{world} + NCCL all-gather merge; e2e: queries copied in on every rank, "
-                                               "merged result read back by rank 0") if world > 1 else "1 GPU",
-                   "l2": "inputs larger than L2 (corpus shard %.1f GB vs 126 MB L2), no flush" % ((hi - lo) * dim * 2 / 1e9)},
-        "e2e": {"value": n_queries / float(e2e_s.item()), "unit": UNIT, "h2d_bytes_per_step": int(h_q.nbytes),
-                "d2h_bytes_per_step": int(e_scores.nbytes + e_ids.nbytes)},
-        "gpu_launches": int(all_launches),
-        "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "dense_search_kernel", "achieved": achieved, "peak": peaks["bf16_tflops"],
-                     "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
-                     "frac_of_sustained_peak": achieved / peaks["bf16_tflops_sustained"], "launches": int(gemm_launches),
-                     "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "algorithmic_flops_per_step": flops,
-                     "gemm_kernel_share_of_step": (gemm_ms / args.steps) / ms_per_step,
-                     "select_kernels_ms_per_step": select_ms / args.steps},
-    }
-    if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = dense_cpu_baseline(corpus, h_q, out, n_docs)
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+        assert np.array_equal(e_out[1], out[1].cpu().numpy())
+        d2h = int(e_out[0].nbytes + e_out[1].nbytes)
+
+    # the reference-facing method: search_knn(query_reps fp32 [Q, d], top_docs) -> (list[list[db id]], fp32 [Q, k]) on every rank
+    api_steps = max(1, min(args.steps, 3))
+    api_s, api_out = ctx.time_wall(lambda: index.search_knn(h_q, K_TOP), api_steps, warmup=1)
+    if rank == 0:
+        assert api_out[0][0][0] == int(out[1][0, 0]) and np.array_equal(api_out[1], out[0].cpu().numpy())
+    digest = result_digest(out[0], out[1]) if rank == 0 else None
+
+    line = None
+    if rank == 0:
+        achieved = flops * args.steps / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+        peak = ctx.peaks["bf16_tflops"]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": dense_config(args, dim),
+            "e2e": {"value": n_queries / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h_q.nbytes), "d2h_bytes_per_step": d2h,
+                    "call": "DenseFlatIndexer.search_arrays(host fp32 queries) -> host rows (rank 0)"},
+            "e2e_api": {"value": n_queries / api_s, "unit": UNIT, "steps": api_steps,
+                        "call": "DenseFlatIndexer.search_knn(query_reps, 1000) [reference indexer.py:210-214] -> (list of db-id lists, scores)"},
+            "result_digest": digest,
+            "gpu_launches": int(all_launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "dense_search_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": ctx.peaks["source"],
+                         "frac_of_sustained_peak": achieved / ctx.peaks["bf16_tflops_sustained"], "launches": int(gemm_launches),
+                         "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "algorithmic_flops_per_step": flops,
+                         "gemm_kernel_share_of_step": (gemm_ms / args.steps) / ms_per_step,
+                         "select_kernels_ms_per_step": select_ms / args.steps,
+                         "note": "peak = measured cuBLAS bf16 burst; the timed region runs the tensor cores for seconds, "
+                                 "so frac_of_sustained_peak (measured back-to-back cuBLAS) is the like-for-like figure"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = dense_cpu_baseline(corpus, h_q, n_docs)
+    del corpus, index, out
+    torch.cuda.empty_cache()
+    return line
 
 
-def dense_cpu_baseline(corpus, h_q, gpu_out, n_docs, sample_docs=200_000, sample_queries=512):
+def dense_cpu_baseline(corpus, h_q, n_docs, sample_docs=200_000, sample_queries=512):
     """fp32 restatement of faiss.IndexFlatIP.search (oracle/dense_oracle.py, torch/MKL sgemm + top-k; faiss-cpu itself is not
     installable here) on a bounded slice of the same corpus; QPS is scaled linearly in N to the full corpus."""
     from oracle import dense_oracle
+    torch.set_num_threads(HOST_CORES)
     nd, nq = min(sample_docs, corpus.shape[0]), min(sample_queries, len(h_q))
     docs = corpus[:nd].float().cpu().numpy()
     qs = torch.from_numpy(h_q[:nq]).to(torch.bfloat16).float().numpy()
+    dense_oracle.flat_ip_search(docs[:20000], qs, K_TOP)     # MKL warm-up
     t0 = time.perf_counter()
-    o_scores, o_ids = dense_oracle.flat_ip_search(docs, qs, K_TOP)
+    dense_oracle.flat_ip_search(docs, qs, K_TOP)
     dt = time.perf_counter() - t0
     return {"value": nq / (dt * n_docs / nd), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"{nq} queries x first {nd} docs in {dt:.1f} s (fp32 restatement of IndexFlatIP, not faiss), scaled "
                       f"linearly in N to {n_docs} docs"}
 
 
-def run_reference_dense(args):
-    rank = env_int("RANK", 0)
-    if rank != 0:
-        return
+def run_b200(args):
+    ctx = Ctx(args)
+    records = []
+    if args.workload in ("both", "sparse"):
+        records.append(("sparse", bench_sparse(args, ctx)))
+    for dim in dense_dims(args):
+        records.append(("dense" if dim == 2048 or args.workload == "dense" else f"dense_{dim}", bench_dense(args, ctx, dim)))
+    if ctx.rank == 0:
+        line = records[0][1]
+        for name, rec in records[1:]:
+            line[name] = rec
+        print(json.dumps(line), flush=True)
+    ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------------- reference arm (CPU)
+
+def reference_dense(args, dim):
     from oracle import dense_oracle
+    torch.set_num_threads(HOST_CORES)
     n_docs = args.n_docs or synth.MSMARCO_DOCS
     n_queries = args.n_queries or synth.MSMARCO_DEV_QUERIES
     nd, nq = min(200_000, n_docs), min(512, n_queries)
-    docs = synth.gen_dense(n_docs, args.dim, seed=1234, row_lo=0, row_hi=nd).numpy()
-    qs = synth.gen_dense(n_queries, args.dim, seed=4321, row_lo=0, row_hi=nq).numpy()
+    docs = synth.gen_dense(n_docs, dim, seed=1234, row_lo=0, row_hi=nd).numpy()
+    qs = synth.gen_dense(n_queries, dim, seed=4321, row_lo=0, row_hi=nq).numpy()
     times = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -485,23 +616,17 @@ def run_reference_dense(args):
             times.append(time.perf_counter() - t0)
     s_per_step = sum(times) / len(times)
     value = nq / (s_per_step * n_docs / nd)
-    sample = (f"{nq} queries x first {nd} docs per step (fp32 restatement of faiss IndexFlatIP: torch/MKL sgemm + top-k), QPS "
-              f"scaled linearly in N to {n_docs} docs")
-    print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": dense_workload_name(n_docs, n_queries, args.dim), "n_docs": n_docs, "n_queries": n_queries,
-                   "k": K_TOP, "dim": args.dim},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+    sample = (f"{nq} queries x first {nd} docs per step (fp32 restatement of faiss IndexFlatIP: torch/MKL sgemm + top-k, "
+              f"{torch.get_num_threads()} threads), QPS scaled linearly in N to {n_docs} docs")
+    return {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": dense_config(args, dim),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
-def run_reference(args):
-    """Reference arm: the CPU port of the reference's sparse retrieval path, all host threads, bounded sample per step."""
-    rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
-    if rank != 0:
-        return
+def reference_sparse(args):
+    """The CPU port of the reference's sparse retrieval path, all host cores, bounded sample per step."""
     from oracle import c_oracle
     n_docs, n_queries, n_terms = sparse_sizes(args)
     dev = "cuda" if torch.cuda.is_available() else "cpu"     # torch RNG only generates the synthetic corpus
@@ -510,26 +635,36 @@ def run_reference(args):
     off, ids, w = c_oracle.build_csr(rows, cols, vals, n_terms)
     del rows, cols, vals
     q_off, q_terms, q_w = (x.cpu().numpy() for x in synth.gen_sparse_queries(n_queries, n_terms=n_terms, device=dev))
-    threads = c_oracle.max_threads()
+    threads = HOST_CORES          # explicit: torchrun exports OMP_NUM_THREADS=1
     sample = min(n_queries, max(threads * 4, 16))
     times = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        c_oracle.sparse_search(off, ids, w, n_docs, q_off[:sample + 1], q_terms, q_w, K_TOP)
+        c_oracle.sparse_search(off, ids, w, n_docs, q_off[:sample + 1], q_terms, q_w, K_TOP, n_threads=threads)
         if i >= args.warmup:
             times.append(time.perf_counter() - t0)
     s_per_step = sum(times) / len(times)
     value = sample / s_per_step
-    line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "n_docs": n_docs, "n_queries": n_queries, "k": K_TOP, "n_terms": n_terms},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample} queries per step over the full index; oracle/sparse_oracle.c (C + OpenMP "
-                                   f"restatement of numba_score_float + select_topk), {threads} threads"},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
+    return {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": sparse_config(args),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{sample} queries per step over the full index; oracle/sparse_oracle.c (C + OpenMP "
+                                       f"restatement of numba_score_float + select_topk), {threads} threads"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def run_reference(args):
+    if env_int("RANK", 0) != 0:
+        return               # under torchrun rank 0 alone runs the CPU arm; the other ranks exit 0 without work
+    records = []
+    if args.workload in ("both", "sparse"):
+        records.append(("sparse", reference_sparse(args)))
+    for dim in dense_dims(args):
+        records.append(("dense" if dim == 2048 or args.workload == "dense" else f"dense_{dim}", reference_dense(args, dim)))
+    line = records[0][1]
+    for name, rec in records[1:]:
+        line[name] = rec
     print(json.dumps(line), flush=True)
 
 
@@ -542,15 +677,16 @@ def main():
     ap.add_argument("--n-docs", type=int, default=0, help="override the corpus size (debug; the headline is 8,841,823)")
     ap.add_argument("--n-queries", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="sparse", choices=["sparse", "dense"],
-                    help="sparse = BASELINE.json configs[1] (default, the headline); dense = configs[2]/[3]")
-    ap.add_argument("--dim", type=int, default=2048, help="dense row width (2048 = Lion-DS-1B, 4096 = Lion-DS-8B)")
+    ap.add_argument("--workload", default="both", choices=["both", "sparse", "dense"],
+                    help="both (default) = sparse configs[1] at the top level + dense configs[2] (and configs[3] at N >= 8) as "
+                         "sub-records; sparse / dense = that workload alone")
+    ap.add_argument("--dim", type=int, default=2048, help="dense row width for --workload dense (2048 = Lion-DS-1B, 4096 = Lion-DS-8B)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
-        (run_reference_dense if args.workload == "dense" else run_reference)(args)
+        run_reference(args)
     else:
-        (run_b200_dense if args.workload == "dense" else run_b200)(args)
+        run_b200(args)
 
 
 if __name__ == "__main__":

@@ -161,12 +161,30 @@ int b200ret_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, void* strea
 /* ------------------------------------------------------------------------------------------------
  * (4) Shard merge: G per-shard top-k lists (as produced above, gathered with an NCCL all-gather)
  * -> one global top-k per query under the same total order (score desc, doc id asc).
- * in_scores/in_ids: [G, n_queries, k] contiguous.  No reference counterpart: the reference asserts
+ * in_scores/in_ids: [G, n_queries, k] contiguous; shard g's ids are all smaller than shard g+1's (doc-range
+ * shards in rank order), ids are full 64-bit.  G*k is bounded by shared memory (b200ret_merge_max_shards).
+ * No reference counterpart: the reference asserts
  * world_size == 1 for retrieval (eval_sparse.py:114, eval_dense.py:191).
  * ---------------------------------------------------------------------------------------------- */
 int b200ret_merge_topk(const float* in_scores, const int64_t* in_ids, int32_t n_shards,
                        int32_t n_queries, int32_t k,
                        float* out_scores, int64_t* out_ids, int32_t* out_counts, void* stream);
+
+/* Packed-key form of the same merge — what the sharded search actually exchanges over NVLink (8 bytes per
+ * candidate instead of 12, one collective instead of two).  A key is
+ *   (order-preserving fp32 score bits << 32) | ~(uint32 GLOBAL doc id),   0 = padding,
+ * so that integer order == (score desc, doc id asc); global doc ids must be < 2^32 - 1.
+ *   b200ret_pack_keys:   rows (scores, ids; id -1 = padding) -> keys            [n elements]
+ *   b200ret_merge_keys:  in_keys [n_shards, n_queries, k] (rows sorted descending, zero padded) ->
+ *                        out_keys [n_queries, k], the k largest per query, sorted descending, zero padded;
+ *                        n_shards <= b200ret_merge_max_shards(k) per call (shared-memory bound; merge in passes)
+ *   b200ret_unpack_keys: keys [n_queries, k] -> rows as b200ret_sparse_search writes them + live counts.  */
+int b200ret_pack_keys(const float* scores, const int64_t* ids, int64_t n, uint64_t* keys, void* stream);
+int32_t b200ret_merge_max_shards(int32_t k);
+int b200ret_merge_keys(const uint64_t* in_keys, int32_t n_shards, int32_t n_queries, int32_t k,
+                       uint64_t* out_keys, void* stream);
+int b200ret_unpack_keys(const uint64_t* keys, int32_t n_queries, int32_t k,
+                        float* out_scores, int64_t* out_ids, int32_t* out_counts, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (5) Result materialisation (HOST pointers only, no device work): write run.json

@@ -41,6 +41,10 @@ PROTOTYPES = {
                                       _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_sz, _c_ptr]),
     "b200ret_f32_to_bf16": (_c_int, [_c_ptr, _c_ptr, _c_i64, _c_ptr]),
     "b200ret_merge_topk": (_c_int, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_ptr, _c_ptr]),
+    "b200ret_pack_keys": (_c_int, [_c_ptr, _c_ptr, _c_i64, _c_ptr, _c_ptr]),
+    "b200ret_merge_max_shards": (_c_i32, [_c_i32]),
+    "b200ret_merge_keys": (_c_int, [_c_ptr, _c_i32, _c_i32, _c_i32, _c_ptr, _c_ptr]),
+    "b200ret_unpack_keys": (_c_int, [_c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_ptr, _c_ptr]),
     "b200ret_write_run_json": (_c_int, [ctypes.c_char_p, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr,
                                         _c_ptr, _c_ptr, _c_ptr, _c_i64, ctypes.POINTER(_c_i64)]),
 }
@@ -67,14 +71,21 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
-        path = os.environ.get("B200RET_LIB") or _build.LIB_PATH   # override: tuning builds of the same sources
-        if not os.path.exists(path):
-            try:
-                _build.build()
-            except Exception as exc:  # no silent fallback: the CUDA library is the product
-                raise RuntimeError(
-                    f"libb200ret.so is missing at {path} and could not be built ({exc}). "
-                    "Run `python -m scaling_retriever_b200.build`; there is no CPU fallback.") from exc
+        path = os.environ.get("B200RET_LIB")                      # override: tuning builds of the same sources
+        if not path:
+            path = _build.LIB_PATH
+            if not _build.is_current():                            # missing, or csrc/ was edited after the last build
+                try:
+                    _build.build()
+                except Exception as exc:  # no silent fallback: the CUDA library is the product
+                    if not os.path.exists(path):
+                        raise RuntimeError(
+                            f"libb200ret.so is missing at {path} and could not be built ({exc}). "
+                            "Run `python -m scaling_retriever_b200.build`; there is no CPU fallback.") from exc
+                    import warnings
+                    warnings.warn(f"libb200ret.so is older than csrc/ and could not be rebuilt ({exc}); using the stale library")
+        elif not os.path.exists(path):
+            raise RuntimeError(f"B200RET_LIB={path} does not exist")
         lib = ctypes.CDLL(path)
         for name, (restype, argtypes) in PROTOTYPES.items():
             fn = getattr(lib, name)   # AttributeError if the .so does not export a declared symbol

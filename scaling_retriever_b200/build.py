@@ -57,14 +57,23 @@ def build(force=False, verbose=False):
     """Compile csrc/*.cu into libb200ret.so unless an up-to-date build exists. Returns the .so path."""
     if not force and is_current():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + _sources()
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
-    if verbose:
-        sys.stderr.write(proc.stderr)
-    with open(STAMP_PATH, "w") as f:
-        f.write(_digest())
+    import fcntl
+    with open(os.path.join(PKG_DIR, ".libb200ret.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)          # ranks of one torchrun job must not compile into the same file concurrently
+        if not force and is_current():            # another process built it while we waited
+            return LIB_PATH
+        tmp = f"{LIB_PATH}.tmp{os.getpid()}"
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + _sources()
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            if os.path.exists(tmp):
+                os.remove(tmp)
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+        if verbose:
+            sys.stderr.write(proc.stderr)
+        os.replace(tmp, LIB_PATH)                 # readers never see a torn .so
+        with open(STAMP_PATH, "w") as f:
+            f.write(_digest())
     return LIB_PATH
 
 

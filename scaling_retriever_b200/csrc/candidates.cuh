@@ -5,9 +5,10 @@
 // whose score is > tau[q] is appended to query q's list (capacity cap = k + docs of the first round).  After the
 // round, select_kernel keeps the k best under the total order (score desc, doc id asc) and sets tau[q] to the k-th
 // score; later documents have larger ids, so a tie with tau can never displace a kept one and `> tau` is exact.
-// Round sizes double, so ~k new candidates per query and round survive on exchangeable data; a list that overflows
-// anyway (adversarial doc order) is flagged and the query is re-run with fixed rounds of the first-round size,
-// which cannot overflow.
+// The docs scored grow ROUND_GROWTH x per round, so about (ROUND_GROWTH - 1) * k new candidates per query and round
+// survive tau on exchangeable data; the capacity is k + max(first-round docs, (ROUND_GROWTH + 1) * k), i.e. at least two k
+// of head-room over that expectation for every k up to B200RET_MAX_K.  A list that overflows anyway (adversarial doc
+// order) is flagged and the query is re-run with fixed rounds of the first-round size, which cannot overflow.
 #pragma once
 #include "common.cuh"
 #include "topk_select.cuh"
@@ -71,7 +72,7 @@ int run_rounds_once(LaunchRound& launch_round, const CandBuffers& b, int32_t cap
         }
         unit = end;
         // geometric schedule: the next round covers (ROUND_GROWTH - 1) x the docs seen so far, so about
-        // (ROUND_GROWTH - 1) * k new candidates per query survive tau on exchangeable data (capacity is >= k + 8 k)
+        // (ROUND_GROWTH - 1) * k new candidates per query survive tau on exchangeable data (capacity: see the header)
         if (!safe) size = unit * (ROUND_GROWTH - 1);
     }
     return launch_select(true, b, cap, k, n_queries, n_active, q_list, doc_id_base, out_scores, out_ids, out_counts, stream);

@@ -544,7 +544,9 @@ static int launch_score(const ScoreParams& sp, cudaStream_t stream) {
     return B200RET_OK;
 }
 
-static int search_cap(int k) { return k + ROUND0_BLOCKS * block_docs_of_shape(); }
+// candidate capacity: the k kept keys + what one round may append — the first round's docs, or for large k the ~(ROUND_GROWTH - 1) * k
+// survivors a geometric round is expected to produce, with a two-k margin (candidates.cuh)
+static int search_cap(int k) { return k + std::max(ROUND0_BLOCKS * block_docs_of_shape(), (ROUND_GROWTH + 1) * k); }
 
 }  // namespace b200ret
 

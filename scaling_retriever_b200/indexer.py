@@ -83,29 +83,50 @@ def _stage_out(staging, name, dev_tensor):
 # dense: embeddings dump (unchanged format) + flat inner-product index
 # ------------------------------------------------------------------------------------------------------------------
 
-def _write_emb_chunk(index_dir, local_rank, chunk_idx, embeddings, embeddings_ids, force_int64=False):
+# embs_{rank}_{chunk}.npy path -> bf16 CUDA tensor of the same rows, kept when the corpus is encoded with keep_on_device=True
+# (SURVEY §8 f1): a DenseFlatIndexer in the same process ingests these instead of re-reading the fp32 files.
+DEVICE_EMBEDDINGS = {}
+
+
+def _write_emb_chunk(index_dir, local_rank, chunk_idx, embeddings, embeddings_ids, force_int64=False, keep_on_device=False,
+                     staging=None):
     """embs_{rank}_{chunk}.npy fp32 [n, d] + ids_{rank}_{chunk}.npy (reference indexer.py:58-70; the hybrid indexer always
-    casts the ids to int64, :796)."""
-    embeddings = np.concatenate(embeddings)
+    casts the ids to int64, :796).  `embeddings` is a list of fp32 CUDA batches: they are concatenated on the device and
+    leave it with ONE copy through pinned memory per chunk (the reference syncs with .cpu() once per batch, :56)."""
+    reps = torch.cat(embeddings) if len(embeddings) > 1 else embeddings[0]
+    if reps.is_cuda:   # bounded pinned staging (256 MB slices), not one pinned buffer of the whole 2 M-doc chunk
+        staging = {} if staging is None else staging
+        embeddings_np = np.empty(tuple(reps.shape), dtype=np.float32)
+        rows = max(1, (256 << 20) // (4 * max(reps.shape[1], 1)))
+        for a in range(0, reps.shape[0], rows):
+            host = _stage_out(staging, "embs", reps[a:a + rows])
+            torch.cuda.current_stream().synchronize()
+            embeddings_np[a:a + rows] = host.numpy()
+    else:
+        embeddings_np = reps.numpy()
     if force_int64 or isinstance(embeddings_ids[0], int):
         embeddings_ids = np.array(embeddings_ids, dtype=np.int64)
-    assert len(embeddings) == len(embeddings_ids), (len(embeddings), len(embeddings_ids))
-    np.save(os.path.join(index_dir, "embs_{}_{}.npy".format(local_rank, chunk_idx)), embeddings)
+    assert len(embeddings_np) == len(embeddings_ids), (len(embeddings_np), len(embeddings_ids))
+    emb_path = os.path.join(index_dir, "embs_{}_{}.npy".format(local_rank, chunk_idx))
+    np.save(emb_path, embeddings_np)
     np.save(os.path.join(index_dir, "ids_{}_{}.npy".format(local_rank, chunk_idx)), embeddings_ids)
+    if keep_on_device and reps.is_cuda:
+        DEVICE_EMBEDDINGS[os.path.abspath(emb_path)] = ops.f32_to_bf16(reps.contiguous())
+    return embeddings_np.shape
 
 
 def store_embs(model, collection_loader, local_rank, index_dir, device,
-               chunk_size=2_000_000, use_fp16=False, is_query=False, idx_to_id=None):
+               chunk_size=2_000_000, use_fp16=False, is_query=False, idx_to_id=None, keep_on_device=False):
     """Encode the corpus and write embs_{rank}_{chunk}.npy / ids_{rank}_{chunk}.npy / plan.json (reference
-    indexer.py:26-97).  The on-disk format is the dense index INPUT and is kept byte-compatible."""
+    indexer.py:26-97).  The on-disk format is the dense index INPUT and is kept byte-compatible.  Encoder outputs are
+    accumulated on the device (no per-batch host sync); `keep_on_device=True` additionally keeps every chunk in HBM as bf16
+    (DEVICE_EMBEDDINGS) so that a search in the same job skips the fp32 .npy round trip."""
     write_freq = chunk_size // collection_loader.batch_size
     if is_first_worker():
         print("write_freq: {}, batch_size: {}, chunk_size: {}".format(write_freq, collection_loader.batch_size, chunk_size))
     dtype = torch.bfloat16 if supports_bfloat16() else torch.float32
     print("Using bfloat16" if dtype == torch.bfloat16 else "Using float32")
-
-    def flush(embeddings, embeddings_ids, chunk_idx):
-        _write_emb_chunk(index_dir, local_rank, chunk_idx, embeddings, embeddings_ids)
+    staging = {}
 
     embeddings, embeddings_ids, chunk_idx = [], [], 0
     for idx, batch in tqdm(enumerate(collection_loader), disable=not is_first_worker(),
@@ -117,16 +138,18 @@ def store_embs(model, collection_loader, local_rank, index_dir, device,
                     raise NotImplementedError
                 reps = _unwrap_model(model).doc_encode(**inputs)
                 text_ids = batch["ids"]
-        embeddings.append(reps.float().cpu().numpy())
+        embeddings.append(reps.float())
         assert isinstance(text_ids, list)
         embeddings_ids.extend(text_ids)
         if (idx + 1) % write_freq == 0:
-            flush(embeddings, embeddings_ids, chunk_idx)
+            _write_emb_chunk(index_dir, local_rank, chunk_idx, embeddings, embeddings_ids, keep_on_device=keep_on_device,
+                             staging=staging)
             embeddings, embeddings_ids = [], []
             chunk_idx += 1
     if len(embeddings) != 0:
-        print("last embedddings shape = {}".format(np.concatenate(embeddings).shape))
-        flush(embeddings, embeddings_ids, chunk_idx)
+        shape = _write_emb_chunk(index_dir, local_rank, chunk_idx, embeddings, embeddings_ids, keep_on_device=keep_on_device,
+                                 staging=staging)
+        print("last embedddings shape = {}".format(tuple(shape)))
         chunk_idx += 1
 
     plan = {"nranks": _world_size(), "num_chunks": chunk_idx, "index_path": os.path.join(index_dir, "model.index")}
@@ -136,10 +159,44 @@ def store_embs(model, collection_loader, local_rank, index_dir, device,
             json.dump(plan, fout)
 
 
+FAISS_FLAT_IP_FOURCC = b"IxFI"
+
+
+def write_faiss_flat_ip(path, corpus_bf16, chunk_rows=262144):
+    """index.dpr in the on-disk layout of faiss.write_index(faiss.IndexFlatIP) (faiss 1.8 impl/index_write.cpp — restated
+    from the published format, faiss itself is not installable here): fourcc "IxFI" | d int32 | ntotal int64 | 2 x int64
+    (1 << 20, unused) | is_trained u8 | metric_type int32 (0 = inner product) | n_floats uint64 | fp32 [ntotal, d]."""
+    n, d = corpus_bf16.shape
+    with open(path, "wb") as f:
+        f.write(FAISS_FLAT_IP_FOURCC)
+        f.write(np.int32(d).tobytes() + np.int64(n).tobytes() + np.int64(1 << 20).tobytes() * 2 + b"\x01" + np.int32(0).tobytes())
+        f.write(np.uint64(n * d).tobytes())
+        for i in range(0, n, chunk_rows):
+            f.write(corpus_bf16[i:i + chunk_rows].float().cpu().numpy().tobytes())
+
+
+def read_faiss_flat_ip(path):
+    """(fp32 [ntotal, d] memory map, d) of a faiss IndexFlatIP file (see write_faiss_flat_ip)."""
+    with open(path, "rb") as f:
+        head = f.read(45)
+    if head[:4] != FAISS_FLAT_IP_FOURCC:
+        raise ValueError(f"{path}: not a faiss IndexFlatIP file (fourcc {head[:4]!r}); only flat inner-product indexes "
+                         "(what DenseFlatIndexer.serialize writes, reference indexer.py:145-158) are supported")
+    d = int(np.frombuffer(head, dtype=np.int32, count=1, offset=4)[0])
+    n = int(np.frombuffer(head, dtype=np.int64, count=1, offset=8)[0])
+    metric = int(np.frombuffer(head, dtype=np.int32, count=1, offset=33)[0])
+    n_floats = int(np.frombuffer(head, dtype=np.uint64, count=1, offset=37)[0])
+    if metric != 0 or n_floats != n * d:
+        raise ValueError(f"{path}: unexpected IndexFlatIP header (metric {metric}, {n_floats} floats for {n} x {d})")
+    return np.memmap(path, dtype=np.float32, mode="r", offset=45, shape=(n, d)), d
+
+
 class DenseIndexer(object):
     """Base class with the reference's (de)serialisation surface (indexer.py:127-188).  `self.index` is a bf16 CUDA
-    tensor [N, d] instead of a faiss object; index.dpr is a .npy of its raw uint16 words, index_meta.dpr the pickled
-    id list exactly as in the reference."""
+    tensor [N, d] instead of a faiss object.  index.dpr is written in faiss's own IndexFlatIP file layout (fp32 rows), so
+    the reference can read what this class writes and vice versa; `serialize(file, fmt="bf16")` writes a compact .npy of the
+    raw bf16 words instead (half the size, read back by deserialize as well).  index_meta.dpr is the pickled id list
+    exactly as in the reference."""
 
     def __init__(self, buffer_size: int = 50000):
         self.buffer_size = buffer_size
@@ -158,7 +215,7 @@ class DenseIndexer(object):
     def search_knn(self, query_vectors: np.array, top_docs: int):
         raise NotImplementedError
 
-    def serialize(self, file: str):
+    def serialize(self, file: str, fmt: str = "faiss"):
         logger.info("Serializing index to %s", file)
         if os.path.isdir(file):
             index_file = os.path.join(file, "index.dpr")
@@ -166,8 +223,15 @@ class DenseIndexer(object):
         else:
             index_file = file + ".index.dpr"
             meta_file = file + ".index_meta.dpr"
-        with open(index_file, "wb") as f:
-            np.save(f, self.index.view(torch.int16).cpu().numpy())
+        if _world_size() > 1:
+            raise NotImplementedError("serialize() of a sharded index: every rank holds only its doc-row range")
+        if fmt == "faiss":
+            write_faiss_flat_ip(index_file, self.index)
+        elif fmt == "bf16":
+            with open(index_file, "wb") as f:
+                np.save(f, self.index.view(torch.int16).cpu().numpy())
+        else:
+            raise ValueError(f"serialize: unknown format {fmt!r}")
         with open(meta_file, mode="wb") as f:
             pickle.dump(self.index_id_to_db_id, f)
 
@@ -185,15 +249,40 @@ class DenseIndexer(object):
         return os.path.isfile(index_file) and os.path.isfile(meta_file)
 
     def deserialize(self, path: str):
+        """Works without a prior init_index (eval_dense.py:194-196 calls deserialize on a fresh object).  Under
+        torch.distributed every rank keeps only its doc-row range of the file."""
         logger.info("Loading index from %s", path)
         index_file, meta_file = self.get_files(path)
         with open(index_file, "rb") as f:
-            words = np.load(f)
-        self.index = torch.from_numpy(words).to(_cuda_device(None)).view(torch.bfloat16)
-        logger.info("Loaded index of type %s and size %d", type(self.index), self.index.shape[0])
+            magic = f.read(6)
+        device = _cuda_device(getattr(self, "device", None))
+        if magic == b"\x93NUMPY":
+            words = np.load(index_file, mmap_mode="r")
+            n, dim = words.shape
+            lo, hi = shard.ShardPlan(n, _world_size()).bounds(_rank())
+            corpus = torch.from_numpy(np.ascontiguousarray(words[lo:hi])).to(device).view(torch.bfloat16)
+        elif magic[:4] == FAISS_FLAT_IP_FOURCC:
+            rows, dim = read_faiss_flat_ip(index_file)
+            n = rows.shape[0]
+            lo, hi = shard.ShardPlan(n, _world_size()).bounds(_rank())
+            corpus = torch.empty((hi - lo, dim), dtype=torch.bfloat16, device=device)
+            step = max(1, (256 << 20) // (4 * dim))
+            for a in range(lo, hi, step):
+                b = min(hi, a + step)
+                corpus[a - lo:b - lo] = ops.f32_to_bf16(torch.from_numpy(np.ascontiguousarray(rows[a:b])).to(device))
+        else:
+            raise ValueError(f"{index_file}: neither a faiss IndexFlatIP file nor the bf16 .npy written by "
+                             f"serialize(fmt='bf16') (first bytes {magic!r})")
+        self.index = corpus
+        self.device = device
+        self.hidden_dim = int(dim)
+        self._row_lo = lo
+        self._n_total = n
+        self._ext = None
+        logger.info("Loaded index of type %s and size %d", type(self.index), n)
         with open(meta_file, "rb") as reader:
             self.index_id_to_db_id = pickle.load(reader)
-        assert len(self.index_id_to_db_id) == self.index.shape[0], "Deserialized index_id_to_db_id should match index size"
+        assert len(self.index_id_to_db_id) == n, "Deserialized index_id_to_db_id should match index size"
 
     def _update_id_mapping(self, db_ids: List):
         self.index_id_to_db_id.extend(db_ids)
@@ -211,6 +300,7 @@ class DenseFlatIndexer(DenseIndexer):
         self.device = device
         self.hidden_dim = None
         self._row_lo = 0
+        self._n_total = 0
         self._staging = {}
         self._ext = None
 
@@ -218,36 +308,63 @@ class DenseFlatIndexer(DenseIndexer):
         self.device = _cuda_device(self.device)
         self.hidden_dim = int(hidden_dim)
         self.index = torch.empty((0, self.hidden_dim), dtype=torch.bfloat16, device=self.device)
+        self._row_lo = 0
+        self._n_total = 0
+
+    def _rows_to_bf16(self, doc_reps, a, b):
+        """Rows [a, b) of the batch as a bf16 CUDA tensor: host fp32 -> device -> cast kernel, or straight from CUDA tensors
+        (fp32 / bf16) when the encoder output never left the device."""
+        if isinstance(doc_reps, torch.Tensor):
+            chunk = doc_reps[a:b].to(self.device)
+            return chunk.contiguous() if chunk.dtype == torch.bfloat16 else ops.f32_to_bf16(chunk.float().contiguous())
+        chunk = torch.from_numpy(np.ascontiguousarray(doc_reps[a:b], dtype=np.float32)).to(self.device)
+        return ops.f32_to_bf16(chunk)
 
     def index_data(self, doc_reps, doc_ids):
+        """Additive like faiss's index.add (reference indexer.py:198-208): rows are appended behind what the index already
+        holds (a second call, or a call after deserialize, extends the corpus and the id list consistently).
+        `doc_reps`: fp32 ndarray [n, d] as in the reference, or a torch tensor (CUDA fp32/bf16: no host round trip).
+        Sharded (world_size > 1): each rank keeps its doc-row range of the batch; only the first batch can be sharded."""
         assert len(doc_reps) == len(doc_ids)
         n = len(doc_reps)
-        plan = shard.ShardPlan(n, _world_size())
-        lo, hi = plan.bounds(_rank())
-        self._row_lo = lo
-        corpus = torch.empty((hi - lo, self.hidden_dim), dtype=torch.bfloat16, device=self.device)
-        n_total = 0
+        n_before = len(self.index_id_to_db_id)
+        if self.hidden_dim is None:
+            self.init_index(doc_reps.shape[1])
+        world = _world_size()
+        if world > 1 and n_before > 0:
+            raise NotImplementedError("sharded DenseFlatIndexer: the corpus must arrive in ONE index_data call (each rank keeps "
+                                      "one contiguous doc-row range); got a second batch")
+        lo, hi = shard.ShardPlan(n, world).bounds(_rank())
+        fresh = torch.empty((hi - lo, self.hidden_dim), dtype=torch.bfloat16, device=self.device)
+        n_total = n_before
         for i in tqdm(range(0, n, self.buffer_size), total=n // self.buffer_size, desc="indexing", disable=not is_first_worker()):
             a, b = max(i, lo), min(i + self.buffer_size, hi)
-            if a < b:   # this slice (partly) belongs to our shard: host fp32 -> device -> bf16 cast kernel
-                chunk = torch.from_numpy(np.ascontiguousarray(doc_reps[a:b], dtype=np.float32)).to(self.device)
-                corpus[a - lo:b - lo] = ops.f32_to_bf16(chunk)
+            if a < b:   # this slice (partly) belongs to our shard
+                fresh[a - lo:b - lo] = self._rows_to_bf16(doc_reps, a, b)
             n_total = self._update_id_mapping(doc_ids[i:i + self.buffer_size])
             logger.info("data indexed %d", n_total)
-        assert n_total == n, (n_total, n)
-        self.index = corpus
+        assert n_total == n_before + n, (n_total, n_before, n)
+        if n_before > 0:
+            self.index = torch.cat([self.index, fresh])
+        else:
+            self.index = fresh
+            self._row_lo = lo
+        self._n_total = n_total
+        self._ext = None
         logger.info("total data indexed %d", n_total)
 
     def search_arrays(self, query_reps, top_docs, host_ranks="all"):
         """(scores fp32 [Q, k] descending, row labels int64 [Q, k], -1 padded) as host numpy arrays.
         `host_ranks="first"` (sharded search only): the merged result is copied to the host of the first worker alone — the
         rank that writes the run file — and the other ranks return (None, None)."""
+        if self.index is None or self.device is None:
+            raise RuntimeError("DenseFlatIndexer: init_index / index_data / deserialize first")
         with torch.cuda.device(self.device):
             q = _stage_in(self._staging, self.device, "queries", query_reps, torch.float32)   # pinned -> device
             q16 = ops.f32_to_bf16(q)
             scores, ids, _ = ops.dense_search(self.index, q16, int(top_docs), doc_id_base=self._row_lo)
             if _world_size() > 1:
-                scores, ids, _ = shard.merge_shards(scores, ids, int(top_docs))
+                scores, ids, _ = shard.merge_shards(scores, ids, int(top_docs), n_docs_total=self._n_total)
             if host_ranks == "first" and not is_first_worker():
                 torch.cuda.current_stream().synchronize()
                 return None, None
@@ -388,6 +505,33 @@ class SparseRetrieval:
             scores = -scores
         return filtered_indexes, scores
 
+    @staticmethod
+    def numba_score_float(inverted_index_ids, inverted_index_floats, indexes_to_retrieve, query_values, threshold, size_collection):
+        """The reference's static scorer (indexer.py:324-344) with its signature and return values — `(filtered_indexes
+        int64[h], -scores[filtered] fp32[h])` for ONE query over dict-like {term: int32 ids} / {term: fp32 weights} — computed
+        by the GPU kernel: the posting lists of the query's terms are uploaded as a small CSR (lists may be in any doc
+        order), scored by `b200ret_sparse_scores` with the reference's arithmetic (fp32 multiply, then add, terms in the
+        given order) and filtered with the strict `> threshold`.  An API-parity entry point for code that calls the kernel
+        directly; the retrieval path scores whole query batches against the HBM-resident index instead."""
+        dev = _cuda_device(None)
+        terms = [int(t) for t in np.asarray(indexes_to_retrieve).tolist()]
+        lists = [(np.asarray(inverted_index_ids[t], dtype=np.int32), np.asarray(inverted_index_floats[t], dtype=np.float32))
+                 for t in terms]
+        n_local = max(len(terms), 1)
+        size_collection = int(size_collection)
+        rows = np.concatenate([a for a, _ in lists]) if lists else np.zeros(0, np.int32)
+        vals = np.concatenate([v for _, v in lists]) if lists else np.zeros(0, np.float32)
+        cols = np.repeat(np.arange(len(lists), dtype=np.int32), [len(a) for a, _ in lists]) if lists else np.zeros(0, np.int32)
+        with torch.cuda.device(dev):
+            index = ops.SparseDeviceIndex.from_coo(torch.from_numpy(rows).to(dev), torch.from_numpy(cols).to(dev),
+                                                   torch.from_numpy(vals).to(dev), n_local, size_collection)
+            off = torch.tensor([0, len(terms)], dtype=torch.int32, device=dev)
+            q_t = torch.arange(len(terms), dtype=torch.int32, device=dev)     # occurrence j of the query -> local list j
+            q_w = torch.from_numpy(np.asarray(query_values, dtype=np.float32)).to(dev)
+            scores = ops.sparse_scores(index, off, q_t, q_w)[0]
+            filtered = torch.nonzero(scores > threshold).flatten()
+            return filtered.cpu().numpy(), (-scores[filtered]).cpu().numpy()
+
     def __init__(self, model, config, dim_voc, device, dataset_name=None, index_d=None, compute_stats=False, is_beir=False,
                  **kwargs):
         self.model = model
@@ -457,7 +601,7 @@ class SparseRetrieval:
             scores, ids, counts = ops.sparse_search(self.device_index, d_off, d_terms, d_w, int(topk), float(threshold),
                                                     doc_id_base=self.doc_id_base)
             if self.shard_plan.world_size > 1:
-                scores, ids, counts = shard.merge_shards(scores, ids, int(topk))
+                scores, ids, counts = shard.merge_shards(scores, ids, int(topk), n_docs_total=self.size_collection)
             if host_ranks == "first" and not is_first_worker():
                 torch.cuda.current_stream().synchronize()
                 return None, None, None
@@ -516,9 +660,13 @@ class SparseRetrieval:
         result arrays (results.LazyRun: inner dicts are built on access, `.to_dict()` gives the eager dict of dicts) —
         the reference spends ~5 s in its per-pair insert loop at 6,980 x 1000 pairs (:429-430)."""
         q_offsets, q_terms, q_weights = pack_queries(sparse_query_vecs)
-        scores, ids, counts = self.search_arrays(q_offsets, q_terms, q_weights, topk, threshold)
-        # search_arrays hands out views of reusable pinned staging buffers: the run owns copies
-        res = LazyRun(qids, np.array(ids), np.array(scores), np.array(counts), self._external_ids())
+        # Sharded search (torchrun, world_size > 1): the merged rows are copied to the host of the first worker only — the rank
+        # that writes run.json / q_stats.json in retrieve() — and the other ranks return an empty run.
+        scores, ids, counts = self.search_arrays(q_offsets, q_terms, q_weights, topk, threshold, host_ranks="first")
+        if scores is None:
+            res = LazyRun([], np.zeros((0, topk), np.int64), np.zeros((0, topk), np.float32), np.zeros(0, np.int32), self._external_ids())
+        else:   # search_arrays hands out views of reusable pinned staging buffers: the run owns copies
+            res = LazyRun(qids, np.array(ids), np.array(scores), np.array(counts), self._external_ids())
         stats = defaultdict(float)
         for n in np.diff(q_offsets).tolist():
             stats["L0_q"] += n / len(qids)
@@ -553,7 +701,8 @@ class HybridIndexer:
     SparseIndexer, the dense half to the embs_/ids_/plan.json shard files of store_embs (reference indexer.py:710-856)."""
 
     def __init__(self, model, sparse_index_dir, dense_index_dir, device, chunk_size=2_000_000, compute_stats=False,
-                 dim_voc=None, force_new=True, filename="array_index.h5py", **kwargs):
+                 dim_voc=None, force_new=True, filename="array_index.h5py", keep_on_device=False, **kwargs):
+        self.keep_on_device = keep_on_device   # also keep the dense chunks in HBM as bf16 (DEVICE_EMBEDDINGS)
         self.model = model
         self.model.eval()
         self.sparse_index_dir = sparse_index_dir
@@ -581,6 +730,7 @@ class HybridIndexer:
         stats = defaultdict(float)
         count = 0
         embeddings, embeddings_ids, chunk_idx = [], [], 0
+        staging = {}
         write_freq = self.chunk_size // collection_loader.batch_size
         with torch.inference_mode():
             for idx, batch in enumerate(tqdm(collection_loader, disable=not is_first_worker())):
@@ -593,15 +743,17 @@ class HybridIndexer:
                 _add_sparse_batch(self.sparse_index, batch_sparse_reps, batch_ids, count, self.world_size, self.rank, doc_ids,
                                   require_all=True)
                 count += len(batch_ids)
-                embeddings.append(batch_dense_reps.float().cpu().numpy())
+                embeddings.append(batch_dense_reps.float())
                 embeddings_ids.extend(batch_ids)
                 if (idx + 1) % write_freq == 0:
-                    _write_emb_chunk(self.dense_index_dir, self.local_rank, chunk_idx, embeddings, embeddings_ids, force_int64=True)
+                    _write_emb_chunk(self.dense_index_dir, self.local_rank, chunk_idx, embeddings, embeddings_ids, force_int64=True,
+                                     keep_on_device=self.keep_on_device, staging=staging)
                     embeddings, embeddings_ids = [], []
                     chunk_idx += 1
         if len(embeddings) != 0:
-            print("last embedddings shape = {}".format(np.concatenate(embeddings).shape))
-            _write_emb_chunk(self.dense_index_dir, self.local_rank, chunk_idx, embeddings, embeddings_ids, force_int64=True)
+            shape = _write_emb_chunk(self.dense_index_dir, self.local_rank, chunk_idx, embeddings, embeddings_ids, force_int64=True,
+                                     keep_on_device=self.keep_on_device, staging=staging)
+            print("last embedddings shape = {}".format(tuple(shape)))
             chunk_idx += 1
         plan = {"nranks": _world_size(), "num_chunks": chunk_idx, "index_path": os.path.join(self.dense_index_dir, "model.index")}
         print("plan: ", plan)
@@ -676,10 +828,13 @@ class HybridRetriever:
         return sparse_query_vecs, dense_query_vecs, qids
 
     def _index_encoded_data(self, doc_vec_files, doc_id_files):
-        doc_reps = np.concatenate([np.load(f) for f in doc_vec_files], axis=0)
+        if all(os.path.abspath(f) in DEVICE_EMBEDDINGS for f in doc_vec_files):   # encoded in this job: bf16 chunks are in HBM
+            doc_reps = torch.cat([DEVICE_EMBEDDINGS[os.path.abspath(f)] for f in doc_vec_files])
+        else:
+            doc_reps = np.concatenate([np.load(f) for f in doc_vec_files], axis=0)
         doc_ids = np.concatenate([np.load(f) for f in doc_id_files]).tolist()
         assert len(doc_reps) == len(doc_ids), (len(doc_reps), len(doc_ids))
-        print("size of doc reps to index: ", doc_reps.shape)
+        print("size of doc reps to index: ", tuple(doc_reps.shape))
         self.dense_index.index_data(doc_reps, doc_ids)
         print("finished indexing")
 

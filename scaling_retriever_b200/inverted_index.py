@@ -160,6 +160,11 @@ class IndexDictOfArray:
             cols = rows.clone()
             vals = torch.empty(0, dtype=torch.float32, device=self.device)
         self._log = []
+        if rows.numel():   # the kernels trust term and row ids: one cheap device reduction each before the sort
+            c_lo, c_hi, r_lo = int(cols.min().item()), int(cols.max().item()), int(rows.min().item())
+            if c_lo < 0 or c_hi >= n_terms or r_lo < 0:
+                raise ValueError(f"add_batch_document: term ids must be in [0, {n_terms}) and rows >= 0 "
+                                 f"(got cols in [{c_lo}, {c_hi}], min row {r_lo})")
         n_docs = max(self.n, int(rows.max().item()) + 1 if rows.numel() else 0)
         self._csr_dev = ops.csr_build(rows, cols, vals, n_terms, n_docs, sort_docs=False)
         self.dim_voc = n_terms
@@ -212,6 +217,12 @@ class IndexDictOfArray:
             import h5py  # optional: the reference's HDF5 layout (inverted_index.py:92-100)
         except ImportError:
             h5py = None
+        if h5py is None:
+            import warnings
+            warnings.warn(f"h5py is not installed: {self.filename} (the reference's HDF5 layout) is NOT written; the index is "
+                          f"saved as the native CSR bundle {CSR_FILES} only, which the unmodified reference cannot load")
+            if os.path.exists(self.filename):
+                os.remove(self.filename)     # a stale HDF5 file of an older index must not outlive the new bundle
         if h5py is not None:
             with h5py.File(self.filename, "w") as f:
                 f.create_dataset("dim", data=int(dim) if dim else len(keys))
@@ -226,13 +237,22 @@ class IndexDictOfArray:
     def device_index(self, doc_lo=0, doc_hi=None):
         """Search-side index on the GPU for doc rows [doc_lo, doc_hi) (default: all; row ids become local to the range):
         doc-sorted CSR + doc-block skip table, slices in bank order.  The canonical CSR of this object is not modified."""
-        off, ids, w = self.finalize()
         n_docs = int(self.n)
-        if doc_lo != 0 or (doc_hi is not None and doc_hi != n_docs):
-            from . import shard
+        sharded = doc_lo != 0 or (doc_hi is not None and doc_hi != n_docs)
+        if sharded and self._csr_dev is None and self._csr_host is not None:
+            # loaded from disk: cut the shard out on the HOST and upload only that (every rank used to upload the whole CSR,
+            # 14 GB at 8.8 M docs, before slicing it on the device)
+            dev = self.device if self.device is not None else torch.device("cuda", torch.cuda.current_device())
             doc_hi = n_docs if doc_hi is None else doc_hi
-            off, ids, w = shard.shard_sparse_csr(off, ids, w, doc_lo, doc_hi)
+            off, ids, w = (torch.as_tensor(a).to(dev) for a in shard_csr_host(*self._csr_host, doc_lo, doc_hi))
             n_docs = doc_hi - doc_lo
+        else:
+            off, ids, w = self.finalize()
+            if sharded:
+                from . import shard
+                doc_hi = n_docs if doc_hi is None else doc_hi
+                off, ids, w = shard.shard_sparse_csr(off, ids, w, doc_lo, doc_hi)
+                n_docs = doc_hi - doc_lo
         try:
             return ops.SparseDeviceIndex.from_csr(off, ids, w, n_docs)
         except Exception as exc:   # lists not ascending (merged multi-rank index): re-sort by (term, doc) on the GPU
@@ -243,6 +263,25 @@ class IndexDictOfArray:
         cols = torch.repeat_interleave(torch.arange(off.numel() - 1, dtype=torch.int32, device=off.device), counts,
                                        output_size=ids.numel())
         return ops.SparseDeviceIndex.from_coo(ids, cols, w, off.numel() - 1, n_docs)
+
+
+def shard_csr_host(off, ids, w, lo, hi, terms_per_chunk=2048):
+    """Host CSR restricted to doc rows [lo, hi) with LOCAL row ids, in bounded-memory chunks of terms (numpy only)."""
+    n_terms = len(off) - 1
+    new_off = np.zeros(n_terms + 1, dtype=np.int64)
+    out_ids, out_w = [], []
+    for t0 in range(0, n_terms, terms_per_chunk):
+        t1 = min(n_terms, t0 + terms_per_chunk)
+        a, b = int(off[t0]), int(off[t1])
+        seg = ids[a:b]
+        keep = (seg >= lo) & (seg < hi)
+        csum = np.concatenate([[0], np.cumsum(keep, dtype=np.int64)])
+        new_off[t0 + 1:t1 + 1] = new_off[t0] + csum[off[t0 + 1:t1 + 1] - a]
+        out_ids.append((seg[keep] - lo).astype(np.int32))
+        out_w.append(w[a:b][keep])
+    ids_out = np.concatenate(out_ids) if out_ids else np.zeros(0, np.int32)
+    w_out = np.concatenate(out_w) if out_w else np.zeros(0, np.float32)
+    return new_off, ids_out, w_out.astype(np.float32, copy=False)
 
 
 def _resize_offsets(off, dim_voc):
@@ -284,7 +323,11 @@ def read_index_dir(index_path, filename="array_index.h5py", dim_voc=None):
     """Posting lists of an index directory as host CSR arrays (term_offsets int64[V+1], doc_ids int32, weights fp32): the
     native csr_*.npy bundle when present, else the reference's HDF5 file (needs h5py).  No doc_ids.pkl involved."""
     paths = [os.path.join(index_path, f) for f in CSR_FILES]
-    if all(os.path.exists(p) for p in paths):
+    h5_path = os.path.join(index_path, filename)
+    have_csr = all(os.path.exists(p) for p in paths)
+    if have_csr and os.path.exists(h5_path) and os.path.getmtime(h5_path) > max(os.path.getmtime(p) for p in paths) + 1.0:
+        have_csr = False     # the directory was re-indexed by the reference (HDF5 only) after the bundle was written: bundle is stale
+    if have_csr:
         off, ids, w = (np.load(p) for p in paths)
         if dim_voc is not None and dim_voc != len(off) - 1:   # the reference trusts dim_voc (inverted_index.py:25-26)
             off = _resize_offsets(off, dim_voc)

@@ -232,10 +232,73 @@ def merge_topk(scores, ids, k):
     if kk != k or ids.shape != scores.shape:
         raise ValueError("scores/ids must both be [n_shards, n_queries, k]")
     dev = scores.device
+    per_pass = max(2, merge_max_shards(k))
+    while n_shards > per_pass:     # large G * k: merge groups of shards first (group order keeps shard order)
+        parts = [merge_topk(scores[a:a + per_pass].contiguous(), ids[a:a + per_pass].contiguous(), k)[:2]
+                 for a in range(0, n_shards, per_pass)]
+        scores, ids = torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts])
+        n_shards = scores.shape[0]
     with torch.cuda.device(dev):
         out_scores = torch.empty((n_queries, k), dtype=torch.float32, device=dev)
         out_ids = torch.empty((n_queries, k), dtype=torch.int64, device=dev)
         out_counts = torch.empty(n_queries, dtype=torch.int32, device=dev)
         _lib.check(lib.b200ret_merge_topk(_ptr(scores), _ptr(ids), n_shards, n_queries, k,
                                           _ptr(out_scores), _ptr(out_ids), _ptr(out_counts), _stream()))
+    return out_scores, out_ids, out_counts
+
+
+def merge_max_shards(k):
+    """Shards one merge pass can take for this k (shared-memory bound of the merge kernels)."""
+    return int(_lib.load().b200ret_merge_max_shards(int(k)))
+
+
+def pack_keys(scores, ids, out=None):
+    """(scores fp32, global ids int64; id -1 = padding) -> packed 64-bit keys (int64 storage), same shape."""
+    lib = _lib.load()
+    _check_cuda("scores", scores, torch.float32)
+    _check_cuda("ids", ids, torch.int64)
+    if scores.shape != ids.shape:
+        raise ValueError("scores/ids shapes differ")
+    keys = torch.empty(scores.shape, dtype=torch.int64, device=scores.device) if out is None else out
+    with torch.cuda.device(scores.device):
+        _lib.check(lib.b200ret_pack_keys(_ptr(scores), _ptr(ids), scores.numel(), _ptr(keys), _stream()))
+    return keys
+
+
+def merge_keys(keys, k):
+    """Packed keys [G, Q, k] (rows sorted descending, zero padded) -> [Q, k] best keys per query, sorted descending.
+    More shards than one pass takes (large G * k) are merged in several passes."""
+    lib = _lib.load()
+    _check_cuda("keys", keys, torch.int64)
+    n_shards, n_queries, kk = keys.shape
+    if kk != k:
+        raise ValueError("keys must be [n_shards, n_queries, k]")
+    per_pass = max(2, merge_max_shards(k))
+    with torch.cuda.device(keys.device):
+        while True:
+            g = keys.shape[0]
+            if g <= per_pass:
+                out = torch.empty((n_queries, k), dtype=torch.int64, device=keys.device)
+                _lib.check(lib.b200ret_merge_keys(_ptr(keys), g, n_queries, k, _ptr(out), _stream()))
+                return out
+            parts = []
+            for a in range(0, g, per_pass):
+                grp = keys[a:a + per_pass].contiguous()
+                out = torch.empty((n_queries, k), dtype=torch.int64, device=keys.device)
+                _lib.check(lib.b200ret_merge_keys(_ptr(grp), grp.shape[0], n_queries, k, _ptr(out), _stream()))
+                parts.append(out)
+            keys = torch.stack(parts)
+
+
+def unpack_keys(keys, k):
+    """Packed keys [Q, k] -> (scores fp32 [Q,k], ids int64 [Q,k], counts int32 [Q]) with (-inf, -1) padding."""
+    lib = _lib.load()
+    _check_cuda("keys", keys, torch.int64)
+    n_queries = keys.shape[0]
+    dev = keys.device
+    with torch.cuda.device(dev):
+        out_scores = torch.empty((n_queries, k), dtype=torch.float32, device=dev)
+        out_ids = torch.empty((n_queries, k), dtype=torch.int64, device=dev)
+        out_counts = torch.empty(n_queries, dtype=torch.int32, device=dev)
+        _lib.check(lib.b200ret_unpack_keys(_ptr(keys), n_queries, k, _ptr(out_scores), _ptr(out_ids), _ptr(out_counts), _stream()))
     return out_scores, out_ids, out_counts

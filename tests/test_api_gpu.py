@@ -317,3 +317,131 @@ def test_dense_indexer_serialize_roundtrip(cuda, tmp_path):
     a_ids, a_scores = index.search_knn(queries, k)
     b_ids, b_scores = loaded.search_knn(queries, k)
     assert a_ids == b_ids and np.array_equal(a_scores, b_scores)
+
+
+def test_static_numba_score_float_shim_matches_reference_golden(golden, cuda):
+    """SURVEY §8b lists the STATIC SparseRetrieval.numba_score_float(ids_dict, vals_dict, col, values, threshold, size_collection)
+    (reference indexer.py:324-344) as a name that must exist: same arguments, same (filtered, -scores) bits as the reference's
+    numba kernel produced for the golden queries (threshold 1.0), computed by the GPU kernel."""
+    off, ids, vals = golden["C_offsets"], golden["C_ids"], golden["C_vals"]
+    n_docs, n_terms = int(golden["C_n_docs"]), int(golden["C_n_terms"])
+    index_ids, index_vals = sparse_oracle.csr_to_dicts(off, ids, vals, n_terms)
+    q_off, q_t, q_w = golden["C_q_offsets"], golden["C_q_terms"], golden["C_q_weights"]
+    for qi in (0, 3, 9, 11):
+        f, neg = SparseRetrieval.numba_score_float(index_ids, index_vals, q_t[q_off[qi]:q_off[qi + 1]], q_w[q_off[qi]:q_off[qi + 1]],
+                                                   threshold=1.0, size_collection=n_docs)
+        assert f.dtype == np.int64 and neg.dtype == np.float32
+        assert np.array_equal(f, golden[f"C_t1_q{qi}_filtered"])
+        assert np.array_equal(neg.view(np.uint32), golden[f"C_t1_q{qi}_neg_scores"].view(np.uint32))
+    f, neg = SparseRetrieval.numba_score_float(index_ids, index_vals, np.zeros(0, np.int32), np.zeros(0, np.float32), 0.0, n_docs)
+    assert len(f) == 0 and len(neg) == 0                       # empty query
+
+
+def test_dense_index_data_is_additive_and_deserialize_needs_no_init(cuda, tmp_path):
+    """faiss's index.add is additive (reference indexer.py:198-208) and eval_dense.py:194-196 calls deserialize() on a fresh
+    DenseFlatIndexer (no init_index): two index_data calls == one; deserialize -> search works; deserialize + index_data extends."""
+    n, d, k = 900, 64, 30
+    g = torch.Generator().manual_seed(11)
+    docs = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=1).numpy()
+    queries = torch.nn.functional.normalize(torch.randn(7, d, generator=g), dim=1).numpy()
+    ids = [f"P{i}" for i in range(n)]
+    one = DenseFlatIndexer()
+    one.init_index(d)
+    one.index_data(docs, ids)
+    two = DenseFlatIndexer()
+    two.init_index(d)
+    two.index_data(docs[:500], ids[:500])
+    two.index_data(docs[500:], ids[500:])
+    assert two.index.shape == one.index.shape and len(two.index_id_to_db_id) == n
+    a, b = one.search_knn(queries, k), two.search_knn(queries, k)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])
+
+    part = DenseFlatIndexer()
+    part.init_index(d)
+    part.index_data(docs[:500], ids[:500])
+    part.serialize(str(tmp_path))
+    with open(tmp_path / "index.dpr", "rb") as f:
+        assert f.read(4) == b"IxFI"                            # faiss IndexFlatIP layout: the reference can read it
+    fresh = DenseFlatIndexer()                                 # no init_index, no device argument
+    fresh.deserialize(str(tmp_path))
+    assert fresh.hidden_dim == d and fresh.index.is_cuda and fresh.index.shape == (500, d)
+    c = fresh.search_knn(queries, k)
+    assert c[0] == part.search_knn(queries, k)[0]
+    fresh.index_data(docs[500:], ids[500:])                    # eval_dense.py:226 after :196: rows are appended
+    e = fresh.search_knn(queries, k)
+    assert e[0] == a[0] and np.array_equal(e[1], a[1])
+
+    compact = str(tmp_path / "compact")
+    os.makedirs(compact)
+    one.serialize(compact, fmt="bf16")
+    back = DenseFlatIndexer()
+    back.deserialize(compact)
+    assert torch.equal(back.index, one.index)
+    with open(tmp_path / "garbage.index.dpr", "wb") as f:
+        f.write(b"not an index at all")
+    with open(tmp_path / "garbage.index_meta.dpr", "wb") as f:
+        pickle.dump([], f)
+    bad = DenseFlatIndexer()
+    bad.get_index_name = lambda: "index"
+    with pytest.raises(ValueError, match="neither a faiss IndexFlatIP file"):
+        bad.deserialize(str(tmp_path / "garbage"))
+
+
+def test_dense_ingestion_from_device_tensors(cuda, tmp_path):
+    """store_embs(keep_on_device=True) keeps every chunk in HBM as bf16 next to the fp32 .npy files, and
+    DenseFlatIndexer.index_data takes CUDA tensors directly — same index as the host round trip."""
+    from scaling_retriever.indexer import DEVICE_EMBEDDINGS
+    n, d = 1000, 64
+    g = torch.Generator().manual_seed(2)
+    docs = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=1)
+    ext_ids = list(range(n))
+    embed_dir = str(tmp_path / "embs")
+    os.makedirs(embed_dir)
+    store_embs(FakeDenseEncoder(docs).to(cuda), make_loader(n, ext_ids), local_rank=0, index_dir=embed_dir, device=cuda,
+               chunk_size=64 * 6, keep_on_device=True)
+    vec_files, id_files = obtain_doc_vec_dir_files(embed_dir)
+    assert all(os.path.abspath(f) in DEVICE_EMBEDDINGS for f in vec_files)
+    host = DenseFlatIndexer()
+    host.init_index(d)
+    host.index_data(np.concatenate([np.load(f) for f in vec_files]), ext_ids)
+    dev_index = DenseFlatIndexer()
+    dev_index.init_index(d)
+    dev_index.index_data(torch.cat([DEVICE_EMBEDDINGS[os.path.abspath(f)] for f in vec_files]), ext_ids)
+    assert torch.equal(host.index, dev_index.index)
+    f32_index = DenseFlatIndexer()
+    f32_index.init_index(d)
+    f32_index.index_data(docs.to(cuda), ext_ids)
+    assert torch.equal(host.index, f32_index.index)
+    assert np.load(id_files[0]).dtype == np.int64
+    for f in vec_files:
+        DEVICE_EMBEDDINGS.pop(os.path.abspath(f))
+
+
+def test_loaded_index_is_sharded_on_the_host(golden, cuda, tmp_path):
+    """IndexDictOfArray.device_index(lo, hi) of an index LOADED from disk cuts the shard out on the host
+    and gives the same search-side index as slicing on the device."""
+    off, ids, vals = golden["C_offsets"], golden["C_ids"], golden["C_vals"]
+    n_docs, n_terms = int(golden["C_n_docs"]), int(golden["C_n_terms"])
+    built = IndexDictOfArray(str(tmp_path), force_new=True, dim_voc=n_terms)
+    built.add_batch_document(ids, np.repeat(np.arange(n_terms), np.diff(off)), vals, n_docs=n_docs)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        built.save()
+    with open(tmp_path / "doc_ids.pkl", "wb") as f:
+        pickle.dump({i: str(i) for i in range(n_docs)}, f)
+    loaded = IndexDictOfArray(str(tmp_path), dim_voc=n_terms)
+    assert loaded._csr_dev is None
+    lo, hi = n_docs // 3, 2 * n_docs // 3
+    a = loaded.device_index(lo, hi)
+    assert loaded._csr_dev is None                               # the full CSR never went to the device
+    b = built.device_index(lo, hi)
+    assert a.n_docs == b.n_docs == hi - lo
+    assert torch.equal(a.term_offsets, b.term_offsets) and torch.equal(a.postings, b.postings) and torch.equal(a.table, b.table)
+
+
+def test_out_of_range_terms_are_rejected_before_the_kernels(cuda):
+    index = IndexDictOfArray(index_path=None, dim_voc=10)
+    index.add_batch_document(np.array([0, 1]), np.array([3, 10]), np.array([1.0, 2.0], dtype=np.float32), n_docs=2)
+    with pytest.raises(ValueError, match="term ids must be in"):
+        index.finalize()

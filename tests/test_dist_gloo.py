@@ -30,6 +30,23 @@ def merge_rows_reference(all_scores, all_ids, k):
     return out_s, out_i, counts
 
 
+def pack_keys_reference(scores, ids):
+    """numpy restatement of b200ret_pack_keys: (order-preserving fp32 bits << 32) | ~uint32(id); id -1 -> 0."""
+    u = np.ascontiguousarray(scores, dtype=np.float32).view(np.uint32)
+    hi = np.where(u & np.uint32(0x80000000), ~u, u | np.uint32(0x80000000)).astype(np.uint64)
+    lo = (~ids.astype(np.uint32)).astype(np.uint64)
+    return np.where(ids >= 0, (hi << np.uint64(32)) | lo, np.uint64(0))
+
+
+def unpack_keys_reference(keys):
+    hi = (keys >> np.uint64(32)).astype(np.uint32)
+    u = np.where(hi & np.uint32(0x80000000), hi & np.uint32(0x7fffffff), ~hi)
+    live = keys != 0
+    scores = np.where(live, u.view(np.float32), np.float32(-np.inf)).astype(np.float32)
+    ids = np.where(live, (~keys.astype(np.uint32)).astype(np.int64), -1)
+    return scores, ids, live.sum(axis=1).astype(np.int32)
+
+
 def _worker(rank, world, port, tmp):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -49,6 +66,20 @@ def _worker(rank, world, port, tmp):
     merged = merge_rows_reference(all_scores.numpy(), all_ids.numpy(), k)
     full = c_oracle.sparse_search(off, ids, w, n_docs, q_off, q_t, q_w, k)
     ok = all(np.array_equal(a, b) for a, b in zip(merged, full))
+
+    # the packed-key exchange (shard.merge_shards): all-to-all of 8-byte keys, per-slice merge, all-gather of the slices.
+    # The GPU kernels (pack / merge_keys / unpack) are restated in numpy here; the collectives are the product's.
+    nq = len(q_off) - 1
+    qs = shard.query_slice(nq, world)
+    keys = np.zeros((world * qs, k), dtype=np.uint64)
+    keys[:nq] = pack_keys_reference(scores, gids)
+    recv = shard.exchange_keys(torch.as_tensor(keys.view(np.int64)), nq)
+    assert recv.shape == (world, qs, k)
+    mine = np.sort(recv.numpy().view(np.uint64).transpose(1, 0, 2).reshape(qs, world * k), axis=1)[:, ::-1][:, :k]
+    got = shard.gather_merged(torch.as_tensor(np.ascontiguousarray(mine).view(np.int64)), nq).numpy().view(np.uint64)
+    u_scores, u_ids, u_counts = unpack_keys_reference(got)
+    ok = ok and np.array_equal(u_ids, full[1]) and np.array_equal(u_scores.view(np.uint32), full[0].view(np.uint32)) \
+        and np.array_equal(u_counts, full[2])
     np.save(os.path.join(tmp, f"ok_{rank}.npy"), np.array([ok]))
     dist.barrier()
     dist.destroy_process_group()
@@ -59,6 +90,26 @@ def test_two_rank_shard_gather_merge_equals_unsharded(tmp_path):
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
         assert bool(np.load(tmp_path / f"ok_{r}.npy")[0])
+
+
+def test_three_rank_exchange_with_ragged_query_slices(tmp_path):
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(3, port, str(tmp_path)), nprocs=3, join=True)     # 17 queries over 3 ranks: slices 6, 6, 5 (+1 pad)
+    for r in range(3):
+        assert bool(np.load(tmp_path / f"ok_{r}.npy")[0])
+
+
+def test_key_packing_roundtrip_and_order():
+    rng = np.random.default_rng(3)
+    s = np.concatenate([rng.normal(size=500).astype(np.float32) * 20, [0.0, -0.0, np.inf, -np.inf, 1e-38, -1e-38]]).astype(np.float32)
+    i = rng.choice(2 ** 32 - 2, size=len(s), replace=False).astype(np.int64)
+    keys = pack_keys_reference(s[None, :], i[None, :])
+    back_s, back_i, c = unpack_keys_reference(keys)
+    assert np.array_equal(back_i[0], i) and np.array_equal(back_s.view(np.uint32), s[None, :].view(np.uint32)) and c[0] == len(s)
+    order = np.argsort(keys[0])[::-1]
+    ref = np.lexsort((i, -s.astype(np.float64)))
+    nz = s != 0           # +0.0 and -0.0 are distinct keys but equal floats
+    assert np.array_equal(order[nz[order]], ref[nz[ref]])
 
 
 def test_merge_reference_total_order():
