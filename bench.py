@@ -362,6 +362,11 @@ def bench_sparse(args, ctx):
     run_json = None
     if rank == 0:
         res, _ = api_out
+        t0 = time.perf_counter()
+        eager = res.to_dict()                           # what a caller that walks every (query, doc) pair pays on top
+        to_dict_s = time.perf_counter() - t0
+        assert len(eager) == len(res)
+        del eager
         assert len(res) == int((out[2] > 0).sum().item())
         first = next(iter(res))
         assert res[first][str(int(out[1][int(first), 0]))] == float(out[0][int(first), 0])
@@ -390,7 +395,10 @@ def bench_sparse(args, ctx):
                                 "[reference indexer.py:405-474] -> (lazy run mapping, stats)",
                         "run_json": run_json,
                         "with_run_json_value": n_queries / (api_s + run_json["seconds"]),
-                        "note": "with_run_json_value adds retrieve()'s run.json write (native formatter) to every call"},
+                        "materialised_value": n_queries / (api_s + to_dict_s),
+                        "note": "with_run_json_value adds retrieve()'s run.json write (native formatter) to every call; "
+                                "materialised_value adds res.to_dict() — the eager dict of 7 M (docid, score) Python pairs the "
+                                "reference builds in its insert loop — for callers that walk every pair"},
             "result_digest": digest,
             "gpu_launches": int(all_launches),
             "clocks": clocks,
@@ -533,6 +541,11 @@ def bench_dense(args, ctx, dim):
     api_s, api_out = ctx.time_wall(lambda: index.search_knn(h_q, K_TOP), api_steps, warmup=1)
     if rank == 0:
         assert api_out[0][0][0] == int(out[1][0, 0]) and np.array_equal(api_out[1], out[0].cpu().numpy())
+        t0 = time.perf_counter()
+        rows = api_out[0].tolist()                      # every row as Python lists (what iterating all rows costs in total)
+        rows_s = time.perf_counter() - t0
+        assert len(rows) == n_queries and len(rows[0]) == K_TOP
+        del rows
     digest = result_digest(out[0], out[1]) if rank == 0 else None
 
     line = None
@@ -546,7 +559,11 @@ def bench_dense(args, ctx, dim):
             "e2e": {"value": n_queries / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h_q.nbytes), "d2h_bytes_per_step": d2h,
                     "call": "DenseFlatIndexer.search_arrays(host fp32 queries) -> host rows (rank 0)"},
             "e2e_api": {"value": n_queries / api_s, "unit": UNIT, "steps": api_steps,
-                        "call": "DenseFlatIndexer.search_knn(query_reps, 1000) [reference indexer.py:210-214] -> (list of db-id lists, scores)"},
+                        "call": "DenseFlatIndexer.search_knn(query_reps, 1000) [reference indexer.py:210-214] -> (rows of db ids "
+                                "gathered on access, scores)",
+                        "materialised_value": n_queries / (api_s + rows_s),
+                        "note": "materialised_value adds turning all 6,980 x 1000 labels into Python lists of ids (CPython object "
+                                "creation), which a caller that iterates every row pays in total"},
             "result_digest": digest,
             "gpu_launches": int(all_launches),
             "clocks": clocks,

@@ -187,6 +187,23 @@ int b200ret_unpack_keys(const uint64_t* keys, int32_t n_queries, int32_t k,
                         float* out_scores, int64_t* out_ids, int32_t* out_counts, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * (4b) Gather-sum scoring over semantic-id codes + exact top-k.
+ * Replaces TermEncoderRetriever.get_doc_scores + torch.topk (scaling_retriever/indexer.py:621-641, :688):
+ *   doc_scores[b, n] = sum_l pred[b, codes[n, l]]   (fp32, summed in code order);   top-k per query, sorted descending.
+ * pred: fp32 [n_queries, n_vocab] (the encoder's lex_encode output); codes: int32 [n_docs, code_len] row-major
+ * (the reference's doc_encodings LongTensor, narrowed), code_len a multiple of 4 (the reference asserts 16/32/64/128),
+ * 16-byte aligned, every code in [0, n_vocab) (callers check).  b200ret_term_scores writes the full [n_queries, n_docs]
+ * matrix (get_doc_scores' return value); b200ret_term_search never materialises it.  Output rows as in
+ * b200ret_sparse_search (ties: lowest doc row first).
+ * ---------------------------------------------------------------------------------------------- */
+size_t b200ret_term_search_workspace_bytes(int32_t n_queries, int32_t k);
+int b200ret_term_search(const float* pred, const int32_t* codes, int32_t n_queries, int32_t n_vocab, int32_t n_docs,
+                        int32_t code_len, int32_t k, float* out_scores, int64_t* out_ids, int32_t* out_counts,
+                        void* workspace, size_t workspace_bytes, void* stream);
+int b200ret_term_scores(const float* pred, const int32_t* codes, int32_t n_queries, int32_t n_vocab, int32_t n_docs,
+                        int32_t code_len, float* out_scores, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * (5) Result materialisation (HOST pointers only, no device work): write run.json
  * {qid: {external doc id: score}} straight from the [n_queries, row_stride] result arrays.
  * Replaces `res[str(qid)][str(doc_ids[id_])] = float(sc)` (scaling_retriever/indexer.py:429-430; the same

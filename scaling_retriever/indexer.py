@@ -5,6 +5,6 @@ both trees, so `scaling_retriever.modeling`, `.dataset`, `.tasks` still come fro
 `utils.utils` and `utils.inverted_index` come from here."""
 from scaling_retriever_b200.indexer import (  # noqa: F401
     DEVICE_EMBEDDINGS, DenseFlatIndexer, DenseIndexer, HybridIndexer, HybridRetriever, L0, SparseIndexer, SparseRetrieval,
-    pack_queries, store_embs)
+    TermEncoderRetriever, pack_queries, store_embs)
 from scaling_retriever_b200.inverted_index import IndexDictOfArray  # noqa: F401
 from scaling_retriever_b200.utils import is_first_worker, obtain_doc_vec_dir_files, supports_bfloat16, to_list  # noqa: F401

@@ -45,6 +45,10 @@ PROTOTYPES = {
     "b200ret_merge_max_shards": (_c_i32, [_c_i32]),
     "b200ret_merge_keys": (_c_int, [_c_ptr, _c_i32, _c_i32, _c_i32, _c_ptr, _c_ptr]),
     "b200ret_unpack_keys": (_c_int, [_c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_ptr, _c_ptr]),
+    "b200ret_term_search_workspace_bytes": (_c_sz, [_c_i32, _c_i32]),
+    "b200ret_term_search": (_c_int, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_ptr,
+                                     _c_ptr, _c_sz, _c_ptr]),
+    "b200ret_term_scores": (_c_int, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_ptr, _c_ptr]),
     "b200ret_write_run_json": (_c_int, [ctypes.c_char_p, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr,
                                         _c_ptr, _c_ptr, _c_ptr, _c_i64, ctypes.POINTER(_c_i64)]),
 }

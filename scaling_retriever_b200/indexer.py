@@ -24,7 +24,7 @@ from tqdm import tqdm
 
 from . import ops, shard
 from .inverted_index import IndexDictOfArray
-from .results import ExternalIds, LazyRun
+from .results import ExternalIds, IdRows, LazyRun
 from .utils import is_first_worker, obtain_doc_vec_dir_files, rank as _rank, supports_bfloat16, to_list, world_size as _world_size
 
 logger = logging.getLogger()
@@ -98,10 +98,11 @@ def _write_emb_chunk(index_dir, local_rank, chunk_idx, embeddings, embeddings_id
         staging = {} if staging is None else staging
         embeddings_np = np.empty(tuple(reps.shape), dtype=np.float32)
         rows = max(1, (256 << 20) // (4 * max(reps.shape[1], 1)))
-        for a in range(0, reps.shape[0], rows):
-            host = _stage_out(staging, "embs", reps[a:a + rows])
-            torch.cuda.current_stream().synchronize()
-            embeddings_np[a:a + rows] = host.numpy()
+        with torch.inference_mode():   # the staging buffer may have been created under the encoder loop's inference mode
+            for a in range(0, reps.shape[0], rows):
+                host = _stage_out(staging, "embs", reps[a:a + rows])
+                torch.cuda.current_stream().synchronize()
+                embeddings_np[a:a + rows] = host.numpy()
     else:
         embeddings_np = reps.numpy()
     if force_int64 or isinstance(embeddings_ids[0], int):
@@ -374,9 +375,9 @@ class DenseFlatIndexer(DenseIndexer):
 
     def search_knn(self, query_reps: np.array, top_docs: int):
         scores, indexes = self.search_arrays(query_reps, top_docs)
-        # reference indexer.py:212: [[index_id_to_db_id[idx] ...]] (a -1 label indexes the last id there; kept identical),
-        # as one object-array gather instead of Q*k Python list lookups
-        top_doc_ids = self.external_ids().obj[indexes].tolist()
+        # reference indexer.py:212: [[index_id_to_db_id[idx] ...]] (a -1 label indexes the last id there; kept identical) as a
+        # sequence of rows gathered on access (results.IdRows) instead of Q*k eager Python list lookups
+        top_doc_ids = IdRows(self.external_ids(), indexes.copy())
         return top_doc_ids, scores.copy()   # search_arrays returns views of reusable pinned staging buffers
 
     def external_ids(self):
@@ -681,6 +682,82 @@ class SparseRetrieval:
                     json.dump(stats, handler)
             _write_run(res, os.path.join(self.out_dir, "run.json"))   # native formatter: same bytes as json.dump(res)
         return res
+
+
+class TermEncoderRetriever:
+    """Retrieval over semantic-id codes (reference indexer.py:615-707): every document is a fixed-length list of term ids,
+    its score for a query is the sum of the query's predicted term scores at those ids, and the k best documents are kept.
+    The gather-sum and the top-k run in one GPU kernel pass per query batch (ops.term_search); the reference's
+    pred_scores[:, doc_encodings] intermediate and the [bz, N] score matrix are never built by retrieve()."""
+
+    def __init__(self, model, args):
+        self.model = model
+        self.model.eval()
+        self.args = args
+
+    def _model_device(self):
+        if hasattr(self.model, "base_model"):
+            return self.model.base_model.device
+        if hasattr(self.model, "encoder_decoder"):
+            return self.model.encoder_decoder.device
+        raise NotImplementedError
+
+    def get_doc_scores(self, pred_scores, doc_encodings):
+        """pred_scores [bz, vocab_size], doc_encodings [N, L] -> doc_scores [bz, N] (reference :621-641), full matrix."""
+        codes = doc_encodings if doc_encodings.dtype == torch.int32 else doc_encodings.to(torch.int32)
+        return ops.term_scores(pred_scores.float().contiguous(), codes.contiguous())
+
+    def retrieve(self, collection_loader, docid_to_smtids, topk, out_dir, use_fp16=False, run_name=None):
+        if is_first_worker():
+            if not os.path.exists(out_dir):
+                os.mkdir(out_dir)
+        docids = list(docid_to_smtids.keys())
+        code_len = len(next(iter(docid_to_smtids.values()))) if docids else 0
+        assert code_len in {16, 32, 64, 128} and all(len(v) == code_len for v in docid_to_smtids.values()), code_len
+        print("length of doc_encodings = {}, docids = {}".format(len(docids), len(docids)))
+        device = _cuda_device(self._model_device())
+        codes = torch.from_numpy(np.asarray(list(docid_to_smtids.values()), dtype=np.int64))
+        vocab_checked = None
+        codes = codes.to(torch.int32).to(device).contiguous()
+        if topk > len(docids):       # torch.topk raises here (reference :688)
+            raise RuntimeError(f"selected index k out of range: topk={topk} > {len(docids)} documents")
+
+        ext = ExternalIds(docids)
+        all_qids, all_ids, all_scores = [], [], []
+        for i, batch in tqdm(enumerate(collection_loader), disable=not is_first_worker(),
+                             desc=f"encode # {len(collection_loader)} seqs", total=len(collection_loader)):
+            with torch.inference_mode():
+                with torch.amp.autocast("cuda", enabled=use_fp16):
+                    inputs = {k: v.to(device) for k, v in batch.items() if k != "queries"}
+                    batch_preds = self.model.lex_encode(**inputs)     # [bz, vocab_size]
+                    if isinstance(batch_preds, tuple):
+                        assert len(batch_preds) == 2 and batch_preds[1] is None, batch_preds
+                        batch_preds = batch_preds[0]
+                    elif not isinstance(batch_preds, torch.Tensor):
+                        raise NotImplementedError
+                pred = batch_preds.float().contiguous()
+                if vocab_checked != pred.shape[1]:                    # the kernel trusts the codes: range-check once
+                    assert codes.numel() == 0 or (int(codes.min()) >= 0 and int(codes.max()) < pred.shape[1]), "doc code out of vocabulary"
+                    vocab_checked = pred.shape[1]
+                top_scores, top_idxes, _ = ops.term_search(pred, codes, int(topk))
+            if not isinstance(batch["queries"], list):
+                raise ValueError("query_ids with type {} is not valid".format(type(batch["queries"])))
+            all_qids.extend(batch["queries"])
+            all_ids.append(top_idxes.cpu().numpy())
+            all_scores.append(top_scores.cpu().numpy())
+
+        k = int(topk)
+        ids = np.concatenate(all_ids) if all_ids else np.zeros((0, k), np.int64)
+        scores = np.concatenate(all_scores) if all_scores else np.zeros((0, k), np.float32)
+        # {qid: {docid: score}} (:690-696): a repeated qid REPLACES its earlier entry there (`qid_to_rankdata[qid] = {}`) while
+        # the key keeps its first-seen position — exactly what this dict comprehension gives
+        last = {qid: pos for pos, qid in enumerate(all_qids)}
+        if len(last) != len(all_qids):
+            keep = list(last.values())
+            all_qids, ids, scores = list(last.keys()), ids[keep], scores[keep]
+        qid_to_rankdata = LazyRun(all_qids, ids, scores, None, ext)
+        _write_run(qid_to_rankdata, os.path.join(out_dir, "run.json" if run_name is None else run_name))
+        return qid_to_rankdata
 
 
 def _write_run(res, path):

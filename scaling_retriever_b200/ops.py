@@ -302,3 +302,35 @@ def unpack_keys(keys, k):
         out_counts = torch.empty(n_queries, dtype=torch.int32, device=dev)
         _lib.check(lib.b200ret_unpack_keys(_ptr(keys), n_queries, k, _ptr(out_scores), _ptr(out_ids), _ptr(out_counts), _stream()))
     return out_scores, out_ids, out_counts
+
+
+def term_scores(pred, codes):
+    """doc_scores[b, n] = sum_l pred[b, codes[n, l]] as a full fp32 [Q, N] matrix (TermEncoderRetriever.get_doc_scores)."""
+    lib = _lib.load()
+    _check_cuda("pred", pred, torch.float32)
+    _check_cuda("codes", codes, torch.int32)
+    n_queries, n_vocab = pred.shape
+    n_docs, code_len = codes.shape
+    with torch.cuda.device(pred.device):
+        out = torch.empty((n_queries, n_docs), dtype=torch.float32, device=pred.device)
+        _lib.check(lib.b200ret_term_scores(_ptr(pred), _ptr(codes), n_queries, n_vocab, n_docs, code_len, _ptr(out), _stream()))
+    return out
+
+
+def term_search(pred, codes, k):
+    """Exact top-k of the gather-sum scores without materialising them: (scores fp32 [Q,k] desc, rows int64 [Q,k], counts)."""
+    lib = _lib.load()
+    _check_cuda("pred", pred, torch.float32)
+    _check_cuda("codes", codes, torch.int32)
+    n_queries, n_vocab = pred.shape
+    n_docs, code_len = codes.shape
+    dev = pred.device
+    with torch.cuda.device(dev):
+        out_scores = torch.empty((n_queries, k), dtype=torch.float32, device=dev)
+        out_ids = torch.empty((n_queries, k), dtype=torch.int64, device=dev)
+        out_counts = torch.empty(n_queries, dtype=torch.int32, device=dev)
+        ws_bytes = lib.b200ret_term_search_workspace_bytes(n_queries, k)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.b200ret_term_search(_ptr(pred), _ptr(codes), n_queries, n_vocab, n_docs, code_len, k,
+                                           _ptr(out_scores), _ptr(out_ids), _ptr(out_counts), _ptr(ws), ws_bytes, _stream()))
+    return out_scores, out_ids, out_counts

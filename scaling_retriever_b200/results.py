@@ -11,7 +11,7 @@ The reference builds the run with one CPython dict insert per (query, doc) pair 
 """
 import ctypes
 import json
-from collections.abc import Mapping
+from collections.abc import Mapping, Sequence
 
 import numpy as np
 
@@ -47,6 +47,33 @@ class ExternalIds:
             self._obj = ext
         return self._obj
 
+    def int_table(self):
+        """int64[size] when every external id is a Python / numpy integer (MS MARCO pids saved as int64 .npy), else None."""
+        if not hasattr(self, "_ints"):
+            self._ints = None
+            src = self._src
+            if isinstance(src, range) and src == range(self.size):
+                self._ints = "identity"
+            elif not isinstance(src, dict) and self.size and all(type(x) is int for x in (src[0], src[-1], src[self.size // 2])):
+                try:
+                    ints = np.asarray(src, dtype=np.int64)
+                    if ints.shape == (self.size,) and all(type(x) is int for x in src):
+                        self._ints = ints
+                except (TypeError, ValueError, OverflowError):
+                    pass
+        return self._ints
+
+    def gather_lists(self, labels):
+        """[[external id of label] ...] as nested Python lists (DenseFlatIndexer.search_knn's return, indexer.py:212; negative
+        labels index from the end like the reference's list).  Integer tables are gathered as int64 (3x faster than through the
+        object array)."""
+        ints = self.int_table()
+        if isinstance(ints, str):          # identity
+            return np.where(labels < 0, labels + self.size, labels).tolist()
+        if ints is not None:
+            return ints[labels].tolist()
+        return self.obj[labels].tolist()
+
     def native(self):
         """('identity', None) | ('ints', int64[size]) | ('strs', (blob uint8, offsets int64[size+1])) | ('none', why):
         the table as the C writer takes it; 'none' when the writer's preconditions do not hold (duplicate external ids
@@ -81,6 +108,37 @@ class ExternalIds:
         offsets = np.zeros(len(strs) + 1, dtype=np.int64)
         offsets[1:] = ends + 1
         return "strs", (blob, offsets)
+
+
+class IdRows(Sequence):
+    """`[[external id ...] per query]` — DenseFlatIndexer.search_knn's first return value (indexer.py:212) — as a read-only
+    sequence over the label array: row i is gathered into a Python list when it is indexed or iterated.  Building all
+    Q * k Python objects eagerly costs ~1 s for 6,980 x 1000 (CPython object creation), 4x the search itself; the reference's
+    callers only iterate the rows once (eval_dense.py:229-241).  Compares equal to the eager list of lists; `.tolist()`
+    materialises it."""
+
+    def __init__(self, ext, labels):
+        self.ext = ext
+        self.labels = labels            # int64 [Q, k], owned
+
+    def __len__(self):
+        return len(self.labels)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        return self.ext.gather_lists(self.labels[i])
+
+    def tolist(self):
+        return self.ext.gather_lists(self.labels)
+
+    def __eq__(self, other):
+        if isinstance(other, IdRows):
+            other = other.tolist()
+        return self.tolist() == other
+
+    def __repr__(self):
+        return f"IdRows({len(self)} rows x {self.labels.shape[1] if self.labels.ndim == 2 else 0})"
 
 
 def _str_blob(strs):

@@ -98,3 +98,23 @@ def test_dense_rejects_bad_shapes(cuda):
         ops.dense_search(d, d[:2].contiguous(), 5)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.dense_search(d.cpu(), d.cpu(), 5)
+
+
+def test_dense_search_matches_exact_construction_golden(cuda):
+    """The exact, tie-free construction of tests/golden/make_golden_dense.py: ids and scores of the tcgen05 kernel must equal
+    the stored int64-computed result bit for bit (single search, and sharded over 3 doc ranges + merge)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dense_golden.npz"))
+    k = int(g["k"])
+    docs = ops.f32_to_bf16(torch.as_tensor(g["docs"].astype(np.float32)).to(cuda))
+    queries = ops.f32_to_bf16(torch.as_tensor(g["queries"]).to(cuda))
+    assert torch.equal(docs.float().cpu(), torch.as_tensor(g["docs"].astype(np.float32)))     # bf16 holds the inputs exactly
+    assert torch.equal(queries.float().cpu(), torch.as_tensor(g["queries"]))
+    s, i, c = ops.dense_search(docs, queries, k)
+    assert np.array_equal(i.cpu().numpy(), g["top_ids"])
+    assert np.array_equal(s.cpu().numpy().view(np.uint32), g["top_scores"].view(np.uint32))
+    assert (c.cpu().numpy() == k).all()
+    bounds = [0, 4100, 8000, docs.shape[0]]
+    parts = [ops.dense_search(docs[a:b].contiguous(), queries, k, doc_id_base=a) for a, b in zip(bounds[:-1], bounds[1:])]
+    ms, mi, _ = ops.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), k)
+    assert np.array_equal(mi.cpu().numpy(), g["top_ids"]) and np.array_equal(ms.cpu().numpy().view(np.uint32), g["top_scores"].view(np.uint32))

@@ -121,3 +121,13 @@ def test_dense_oracle_is_exact_topk():
     assert np.all(np.diff(scores[:, :5], axis=1) <= 0)
     for i in range(7):
         assert np.array_equal(labels[i, :5], np.argsort(-(qs[i] @ docs[:5].T), kind="stable"))
+
+
+def test_dense_oracle_matches_exact_construction():
+    """tests/golden/dense_golden.npz (make_golden_dense.py): inner products exactly representable and tie-free by construction,
+    so any correct IndexFlatIP must reproduce the stored ids and scores bit for bit — the restatement does."""
+    import os
+    from oracle import dense_oracle
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dense_golden.npz"))
+    scores, ids = dense_oracle.flat_ip_search(g["docs"].astype(np.float32), g["queries"], int(g["k"]))
+    assert np.array_equal(ids, g["top_ids"]) and np.array_equal(scores.view(np.uint32), g["top_scores"].view(np.uint32))
