@@ -204,6 +204,18 @@ int b200ret_term_scores(const float* pred, const int32_t* codes, int32_t n_queri
                         int32_t code_len, float* out_scores, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * (4c) Rank metrics over the result rows (quick regression checks without the run.json -> pytrec_eval round trip of
+ * scaling_retriever/utils/metrics.py:22-42): per query, reciprocal rank of the first relevant row among the first
+ * `mrr_cut` rows (mrr_k's truncate_run + trec_eval recip_rank) and recall at up to 8 cut-offs (trec_eval recall_<c>).
+ * ids/counts: search output rows [n_queries, k] (sorted by score desc; counts NULL = k live rows everywhere);
+ * rel_offsets int64 [n_queries + 1] / rel_ids int64 (ascending per query): the relevant row labels of each query.
+ * out_rr fp32 [n_queries]; out_recall fp32 [n_queries, n_cuts] (0 for queries without relevant docs).
+ * ---------------------------------------------------------------------------------------------- */
+int b200ret_rank_metrics(const int64_t* ids, const int32_t* counts, int32_t n_queries, int32_t k,
+                         const int64_t* rel_offsets, const int64_t* rel_ids, int32_t mrr_cut,
+                         const int32_t* recall_cuts_host, int32_t n_cuts, float* out_rr, float* out_recall, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * (5) Result materialisation (HOST pointers only, no device work): write run.json
  * {qid: {external doc id: score}} straight from the [n_queries, row_stride] result arrays.
  * Replaces `res[str(qid)][str(doc_ids[id_])] = float(sc)` (scaling_retriever/indexer.py:429-430; the same

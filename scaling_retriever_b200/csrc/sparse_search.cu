@@ -29,6 +29,7 @@
 //     every lane emits its hits (candidates.cuh: rounds of growing size, radix-select cut to k between rounds,
 //     overflow -> safe re-run).
 #include <cstdlib>
+#include <type_traits>
 
 #include "candidates.cuh"
 
@@ -47,6 +48,29 @@ constexpr int ROUND0_BLOCKS = B200RET_ROUND0_BLOCKS;   // first round / safe-sch
 #define B200RET_BATCH_STEPS 2
 #endif
 constexpr int STEP_ROWS = 4;                     // rows (of 32 postings) fetched per pipeline step
+// Slice-descriptor layout in the warp's control area (tuning knob): how the cursor reads (begin, end, query weight) of the
+// next slice — 0: three arrays, three broadcast LDS.32 (3 data-pipe wavefronts per slice); 1: {begin, end} pairs + weight
+// array, LDS.64 + LDS.32 (2 wavefronts); 2: {begin, end, weight, -} records, one LDS.128 (1 wavefront; 128 B more per buffer)
+#ifndef B200RET_DESC_MODE
+#define B200RET_DESC_MODE 1
+#endif
+constexpr int DESC_MODE = B200RET_DESC_MODE;
+// Row-liveness predicates of a step (tuning knob): 0 = four unsigned compares of rel + 32 r against len (3 adds + 4 setp),
+// 1 = one subtraction + compares against immediates (1 sub + 4 setp)
+#ifndef B200RET_PRED_MODE
+#define B200RET_PRED_MODE 1
+#endif
+// Tile sweep (tuning knob): 1 = blocks that lie entirely inside the collection skip the per-document bound checks;
+// 2 = additionally clear unconditionally and branch only for lanes with a hit
+#ifndef B200RET_ADV_MODE        // cursor advance (tuning knob): 1 = fused predicate compares, bit-reversed pending mask
+#define B200RET_ADV_MODE 1
+#endif
+#ifndef B200RET_SWEEP_FAST
+#define B200RET_SWEEP_FAST 2
+#endif
+constexpr int DESC_BUF_WORDS = DESC_MODE >= 2 ? 128 : 96;     // one descriptor buffer (two are used alternately)
+// mode 3 = mode 2 records, and the staged term ids / query weights of the group after the next live in the unused 4th words
+// of the records of buffer 0 / buffer 1 instead of an area of their own (same 1088 bytes per warp as modes 0 and 1)
 
 // Kernel shape: one CTA of WARPS warps per SM, BD docs per warp-private score tile (BD * 4 bytes of shared memory).
 constexpr int SCORE_WARPS = B200RET_SCORE_WARPS;
@@ -63,8 +87,15 @@ struct WarpStash {
     int pad[2];
 };
 enum : unsigned { K_VALID = 1, K_LAST = 2, K_MARKED = 4, A_VALID = 8, A_LAST = 16, B_VALID = 32, B_LAST = 64, N_VALID = 128 };
-constexpr int CTRL_DESC = 0, CTRL_TERMS = 192, CTRL_STASH = 256;                        // word offsets
-constexpr int CTRL_WORDS = CTRL_STASH + static_cast<int>(sizeof(WarpStash) / 4);       // 272 words = 1088 bytes per warp
+constexpr int CTRL_DESC = 0, CTRL_TERMS = 2 * DESC_BUF_WORDS, CTRL_STASH = CTRL_TERMS + (DESC_MODE == 3 ? 0 : 64);   // word offsets
+// word index (from the start of the control area) of lane j's staged term id / query weight
+__device__ __forceinline__ constexpr int stage_t(int j) { return DESC_MODE == 3 ? 4 * j + 3 : CTRL_TERMS + j; }
+__device__ __forceinline__ constexpr int stage_w(int j) { return DESC_MODE == 3 ? DESC_BUF_WORDS + 4 * j + 3 : CTRL_TERMS + 32 + j; }
+constexpr int CTRL_WORDS = CTRL_STASH + static_cast<int>(sizeof(WarpStash) / 4);       // 272 words = 1088 bytes per warp (modes 0, 1)
+// word index of (begin, end, weight) of slice j inside a descriptor buffer
+__device__ __forceinline__ constexpr int desc_beg(int j) { return DESC_MODE == 0 ? j : (DESC_MODE == 1 ? 2 * j : 4 * j); }
+__device__ __forceinline__ constexpr int desc_end(int j) { return DESC_MODE == 0 ? 32 + j : (DESC_MODE == 1 ? 2 * j + 1 : 4 * j + 1); }
+__device__ __forceinline__ constexpr int desc_qw(int j) { return DESC_MODE >= 2 ? 4 * j + 2 : 64 + j; }
 constexpr size_t SCORE_SMEM = static_cast<size_t>(SCORE_WARPS) * (BLOCK_DOCS * sizeof(float) + CTRL_WORDS * sizeof(uint32_t));
 static_assert(BLOCK_DOCS % 128 == 0, "tile sweep uses 128-bit accesses by 32 lanes");
 static_assert(SCORE_SMEM <= 227 * 1024, "exceeds the shared memory of one SM");
@@ -113,19 +144,44 @@ __device__ __forceinline__ void sweep_tile(const ScoreParams& p, float* acc, int
         unsigned mask[(CHUNKS + 7) / 8];
 #pragma unroll
         for (int wd = 0; wd < (CHUNKS + 7) / 8; ++wd) mask[wd] = 0u;
+        auto scan = [&](auto bounded) {
 #pragma unroll
-        for (int ch = 0; ch < CHUNKS; ++ch) {
-            const int i = ch * 128 + lane * 4;
-            float4 v = *reinterpret_cast<const float4*>(acc + i);
-            const unsigned h = ((v.x > tq) && (i < limit) ? 1u : 0u) | ((v.y > tq) && (i + 1 < limit) ? 2u : 0u) |
-                               ((v.z > tq) && (i + 2 < limit) ? 4u : 0u) | ((v.w > tq) && (i + 3 < limit) ? 8u : 0u);
-            if (!(h & 1u)) v.x = 0.f;
-            if (!(h & 2u)) v.y = 0.f;
-            if (!(h & 4u)) v.z = 0.f;
-            if (!(h & 8u)) v.w = 0.f;
-            *reinterpret_cast<float4*>(acc + i) = v;
-            mask[ch >> 3] |= h << ((ch & 7) * 4);
-        }
+            for (int ch = 0; ch < CHUNKS; ++ch) {
+                const int i = ch * 128 + lane * 4;
+                float4 v = *reinterpret_cast<const float4*>(acc + i);
+                unsigned h;
+                if (decltype(bounded)::value) {
+                    h = ((v.x > tq) && (i < limit) ? 1u : 0u) | ((v.y > tq) && (i + 1 < limit) ? 2u : 0u) |
+                        ((v.z > tq) && (i + 2 < limit) ? 4u : 0u) | ((v.w > tq) && (i + 3 < limit) ? 8u : 0u);
+                } else if (B200RET_SWEEP_FAST >= 2) {
+                    // Once tau has risen almost no document beats it: clear the four slots unconditionally (the store does not
+                    // wait for the load) and only a lane whose maximum beats tau takes the branch that puts its hits back.
+                    *reinterpret_cast<float4*>(acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) > tq) {
+                        h = (v.x > tq ? 1u : 0u) | (v.y > tq ? 2u : 0u) | (v.z > tq ? 4u : 0u) | (v.w > tq ? 8u : 0u);
+                        if (h & 1u) acc[i] = v.x;
+                        if (h & 2u) acc[i + 1] = v.y;
+                        if (h & 4u) acc[i + 2] = v.z;
+                        if (h & 8u) acc[i + 3] = v.w;
+                        mask[ch >> 3] |= h << ((ch & 7) * 4);
+                    }
+                    continue;
+                } else {
+                    h = (v.x > tq ? 1u : 0u) | (v.y > tq ? 2u : 0u) | (v.z > tq ? 4u : 0u) | (v.w > tq ? 8u : 0u);
+                }
+                if (!(h & 1u)) v.x = 0.f;
+                if (!(h & 2u)) v.y = 0.f;
+                if (!(h & 4u)) v.z = 0.f;
+                if (!(h & 8u)) v.w = 0.f;
+                *reinterpret_cast<float4*>(acc + i) = v;
+                mask[ch >> 3] |= h << ((ch & 7) * 4);
+            }
+        };
+        // only the last block of the collection is partial: every other item skips the per-document bound checks (warp-uniform)
+        if (B200RET_SWEEP_FAST && limit == BD)
+            scan(std::false_type{});
+        else
+            scan(std::true_type{});
         int mine = 0;
 #pragma unroll
         for (int wd = 0; wd < (CHUNKS + 7) / 8; ++wd) mine += __popc(mask[wd]);
@@ -229,35 +285,35 @@ struct FetchStages {
         }
         st.b_g = g;
         flags &= ~B_LAST;
-        int32_t* tb_t = reinterpret_cast<int32_t*>(ctrl + CTRL_TERMS);
-        float* tb_w = reinterpret_cast<float*>(ctrl + CTRL_TERMS + 32);
+        int32_t* tb_t = reinterpret_cast<int32_t*>(ctrl + stage_t(lane));      // lane-private staging slots
+        float* tb_w = reinterpret_cast<float*>(ctrl + stage_w(lane));
         if ((flags & B_VALID) && g + 32 >= qe) flags |= B_LAST;
-        if ((flags & B_VALID) && g + static_cast<int>(lane) < qe) {      // lane-private staging slots
-            cp_async4(tb_t + lane, p.q_terms + g + lane);
-            cp_async4(tb_w + lane, p.q_weights + g + lane);
+        if ((flags & B_VALID) && g + static_cast<int>(lane) < qe) {
+            cp_async4(tb_t, p.q_terms + g + lane);
+            cp_async4(tb_w, p.q_weights + g + lane);
         } else {
-            tb_t[lane] = -1;
-            tb_w[lane] = 0.f;
+            *tb_t = -1;
+            *tb_w = 0.f;
         }
     }
     // a <- b: issue the two skip-table copies of every term of the group into descriptor buffer `buf` (requires b's term
     // ids to have landed)
     __device__ __forceinline__ void stage_table(unsigned& flags, uint32_t* buf) {
         const int blk = st.b_blk, bq = st.b_q;
-        const int t = reinterpret_cast<const int32_t*>(ctrl + CTRL_TERMS)[lane];
-        const uint32_t qw_bits = ctrl[CTRL_TERMS + 32 + lane];
+        const int t = static_cast<int32_t>(ctrl[stage_t(lane)]);
+        const uint32_t qw_bits = ctrl[stage_w(lane)];
         __syncwarp();
         st.a_q = bq;
         st.a_blk = blk;
         flags = (flags & ~(A_VALID | A_LAST)) | ((flags & B_VALID) ? A_VALID : 0u) | ((flags & B_LAST) ? A_LAST : 0u);
-        buf[64 + lane] = qw_bits;     // query weight
+        buf[desc_qw(lane)] = qw_bits;     // query weight
         if ((flags & A_VALID) && t >= 0) {
             const uint32_t* e = p.table + static_cast<size_t>(t) * p.table_stride + blk;
-            cp_async4(buf + lane, e);
-            cp_async4(buf + 32 + lane, e + 1);
+            cp_async4(buf + desc_beg(lane), e);
+            cp_async4(buf + desc_end(lane), e + 1);
         } else {
-            buf[lane] = 0;
-            buf[32 + lane] = 0;
+            buf[desc_beg(lane)] = 0;
+            buf[desc_end(lane)] = 0;
         }
     }
 };
@@ -301,8 +357,8 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
     uint32_t* const ctrl = reinterpret_cast<uint32_t*>(smem_acc + SCORE_WARPS * BD) + warp * CTRL_WORDS;
     const WarpStash& st = *reinterpret_cast<const WarpStash*>(ctrl + CTRL_STASH);
     // descriptor buffer of the group being streamed: starts at buffer 1 so that the first install flips it to buffer 0
-    const uint32_t desc_s01 = 2u * static_cast<uint32_t>(__cvta_generic_to_shared(ctrl + CTRL_DESC)) + 96u * 4u;
-    uint32_t desc_s = static_cast<uint32_t>(__cvta_generic_to_shared(ctrl + CTRL_DESC)) + 96u * 4u;
+    const uint32_t desc_s01 = 2u * static_cast<uint32_t>(__cvta_generic_to_shared(ctrl + CTRL_DESC)) + DESC_BUF_WORDS * 4u;
+    uint32_t desc_s = static_cast<uint32_t>(__cvta_generic_to_shared(ctrl + CTRL_DESC)) + DESC_BUF_WORDS * 4u;
     const uint32_t acc_s = static_cast<uint32_t>(__cvta_generic_to_shared(acc));
     const uint2* __restrict__ const g_post = p.postings + lane;     // lane-private base: address = base + row position
 
@@ -327,6 +383,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
             ".reg .pred adv, have, take, dead;\n\t"
             ".reg .u32 j, t, a;\n\t"
             "setp.ge.u32 adv, %0, %2;\n\t"                  // c_row >= c_end : current slice exhausted
+#if B200RET_ADV_MODE == 0
             "setp.ne.u32 have, %4, 0;\n\t"
             "and.pred take, adv, have;\n\t"
             "not.pred have, have;\n\t"
@@ -335,11 +392,31 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
             "clz.b32 j, t;\n\t"                             // index of the lowest pending slice
             "add.u32 t, %4, -1;\n\t"
             "@take and.b32 %4, %4, t;\n\t"
+#else       // `pending` is kept BIT-REVERSED (slice j <-> bit 31 - j): the next slice is the count of leading zeros
+            "setp.ne.and.u32 take, %4, 0, adv;\n\t"
+            "setp.eq.and.u32 dead, %4, 0, adv;\n\t"         // exhausted and nothing pending: empty step
+            "clz.b32 j, %4;\n\t"                            // index of the lowest pending slice (32 when none: loads predicated off)
+            "shr.u32 t, 0x80000000, j;\n\t"
+            "@take xor.b32 %4, %4, t;\n\t"
+#endif
+#if B200RET_DESC_MODE == 0
             "shl.b32 a, j, 2;\n\t"
             "add.u32 a, a, %6;\n\t"
             "@take ld.shared.u32 %1, [a];\n\t"              // c_beg
             "@take ld.shared.u32 %2, [a + 128];\n\t"        // c_end
             "@take ld.shared.f32 %3, [a + 256];\n\t"        // c_qw
+#elif B200RET_DESC_MODE == 1
+            "shl.b32 a, j, 3;\n\t"
+            "add.u32 a, a, %6;\n\t"
+            "@take ld.shared.v2.u32 {%1, %2}, [a];\n\t"     // {c_beg, c_end}
+            "shl.b32 a, j, 2;\n\t"
+            "add.u32 a, a, %6;\n\t"
+            "@take ld.shared.f32 %3, [a + 256];\n\t"        // c_qw
+#else       // modes 2 and 3
+            "shl.b32 a, j, 4;\n\t"
+            "add.u32 a, a, %6;\n\t"
+            "@take ld.shared.v4.b32 {%1, %2, %3, j}, [a];\n\t"  // {c_beg, c_end, c_qw, -}
+#endif
             "@take and.b32 %0, %1, 0xffffffe0;\n\t"         // c_row = c_beg rounded down to a row
             "sub.u32 %5, %2, %1;\n\t"
             "@dead mov.u32 %5, 0;\n\t"                      // len
@@ -366,6 +443,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
             ".reg .u32 t0, t1, t2, t3;\n\t"
             "shr.u32 t0, %11, 31;\n\t"
             "add.u32 t0, t0, %8;\n\t"
+#if B200RET_PRED_MODE == 0
             "add.u32 t1, t0, 32;\n\t"
             "add.u32 t2, t0, 64;\n\t"
             "add.u32 t3, t0, 96;\n\t"
@@ -373,6 +451,15 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
             "setp.lt.u32 p1, t1, %9;\n\t"
             "setp.lt.u32 p2, t2, %9;\n\t"
             "setp.lt.u32 p3, t3, %9;\n\t"
+#else       // u = len - rel as a SIGNED count of postings from this lane's row-0 position to the slice end: row r >= 1 is live iff
+            // u > 32 r (lanes before the slice begin have rel = -x, u = len + x; lanes past the end have u <= 0); row 0 also
+            // needs rel >= 0, i.e. the unsigned rel < len
+            "sub.s32 t1, %9, t0;\n\t"
+            "setp.lt.u32 p0, t0, %9;\n\t"
+            "setp.gt.s32 p1, t1, 32;\n\t"
+            "setp.gt.s32 p2, t1, 64;\n\t"
+            "setp.gt.s32 p3, t1, 96;\n\t"
+#endif
             "@p0 " B200RET_LDNC ".v2.b32 {%0, %4}, [%10];\n\t"          // one posting = {doc id, weight bits}
             "@p1 " B200RET_LDNC ".v2.b32 {%1, %5}, [%10 + 256];\n\t"
             "@p2 " B200RET_LDNC ".v2.b32 {%2, %6}, [%10 + 512];\n\t"
@@ -402,6 +489,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
             ".reg .pred p0, p1, p2, p3;\n\t"
             ".reg .f32 a0, a1, a2, a3, v0, v1, v2, v3;\n\t"
             ".reg .u32 t1, t2, t3;\n\t"
+#if B200RET_PRED_MODE == 0
             "add.u32 t1, %9, 32;\n\t"
             "add.u32 t2, %9, 64;\n\t"
             "add.u32 t3, %9, 96;\n\t"
@@ -409,6 +497,13 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
             "setp.lt.u32 p1, t1, %10;\n\t"
             "setp.lt.u32 p2, t2, %10;\n\t"
             "setp.lt.u32 p3, t3, %10;\n\t"
+#else
+            "sub.s32 t1, %10, %9;\n\t"
+            "setp.lt.u32 p0, %9, %10;\n\t"
+            "setp.gt.s32 p1, t1, 32;\n\t"
+            "setp.gt.s32 p2, t1, 64;\n\t"
+            "setp.gt.s32 p3, t1, 96;\n\t"
+#endif
             "@p0 ld.shared.f32 a0, [%0];\n\t"
             "@p1 ld.shared.f32 a1, [%1];\n\t"
             "@p2 ld.shared.f32 a2, [%2];\n\t"
@@ -491,15 +586,16 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
             __syncwarp();
             const unsigned gen = st.gen;
             const int a_q = st.a_q, a_blk = st.a_blk;
-            const uint32_t* buf = ctrl + CTRL_DESC + (gen & 1u) * 96;
-            pending = __ballot_sync(FULL, buf[32 + lane] > buf[lane]);   // non-empty slices, ascending term order
+            const uint32_t* buf = ctrl + CTRL_DESC + (gen & 1u) * DESC_BUF_WORDS;
+            pending = __ballot_sync(FULL, buf[desc_end(lane)] > buf[desc_beg(lane)]);   // non-empty slices, ascending term order
+            if (B200RET_ADV_MODE) pending = __brev(pending);
             desc_s = desc_s01 - desc_s;                       // the cursor reads slice j's descriptor with 3 broadcast LDS.32
             __syncwarp();                                     // stash: reads above, writes below
             fs.st.k_q = a_q;
             fs.st.k_blk = a_blk;
             flags = (flags & ~(K_VALID | K_LAST | K_MARKED)) | K_VALID | ((flags & A_LAST) ? K_LAST : 0u);
             fs.want_claim = false;
-            fs.stage_table(flags, ctrl + CTRL_DESC + ((gen + 1u) & 1u) * 96);
+            fs.stage_table(flags, ctrl + CTRL_DESC + ((gen + 1u) & 1u) * DESC_BUF_WORDS);
             fs.stage_terms(flags, __shfl_sync(FULL, nn_item, 0));
             fs.st.gen = gen + 1u;
             fs.st.flags = flags;

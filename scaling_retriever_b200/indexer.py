@@ -365,6 +365,12 @@ class DenseFlatIndexer(DenseIndexer):
             q16 = ops.f32_to_bf16(q)
             scores, ids, _ = ops.dense_search(self.index, q16, int(top_docs), doc_id_base=self._row_lo)
             if _world_size() > 1:
+                if host_ranks == "first" and self._n_total < shard.KEY_ID_LIMIT:
+                    key = (scores.shape[0], int(top_docs))
+                    if self._staging.get("shared_rows_key") != key:
+                        self._staging["shared_rows"] = shard.SharedHostRows(*key)
+                        self._staging["shared_rows_key"] = key
+                    return shard.merge_shards_to_first_host(scores, ids, int(top_docs), self._staging["shared_rows"])[:2]
                 scores, ids, _ = shard.merge_shards(scores, ids, int(top_docs), n_docs_total=self._n_total)
             if host_ranks == "first" and not is_first_worker():
                 torch.cuda.current_stream().synchronize()
@@ -602,6 +608,10 @@ class SparseRetrieval:
             scores, ids, counts = ops.sparse_search(self.device_index, d_off, d_terms, d_w, int(topk), float(threshold),
                                                     doc_id_base=self.doc_id_base)
             if self.shard_plan.world_size > 1:
+                if host_ranks == "first" and self.size_collection < shard.KEY_ID_LIMIT:
+                    # every GPU copies its merged query slice into host rows shared with the first worker (own PCIe link each)
+                    host = self._shared_rows(scores.shape[0], int(topk))
+                    return shard.merge_shards_to_first_host(scores, ids, int(topk), host)[:3]
                 scores, ids, counts = shard.merge_shards(scores, ids, int(topk), n_docs_total=self.size_collection)
             if host_ranks == "first" and not is_first_worker():
                 torch.cuda.current_stream().synchronize()
@@ -609,6 +619,13 @@ class SparseRetrieval:
             out = [self._stage_out(name, t) for name, t in (("scores", scores), ("ids", ids), ("counts", counts))]
             torch.cuda.current_stream().synchronize()
             return tuple(o.numpy() for o in out)
+
+    def _shared_rows(self, n_queries, k):
+        key = (n_queries, k)
+        if self._staging.get("shared_rows_key") != key:
+            self._staging["shared_rows"] = shard.SharedHostRows(n_queries, k)
+            self._staging["shared_rows_key"] = key
+        return self._staging["shared_rows"]
 
     def _stage_in(self, name, host_array, dtype):
         return _stage_in(self._staging, self._cuda, name, host_array, dtype)

@@ -8,8 +8,9 @@ Mirrors scaling_retriever/utils/inverted_index.py of the reference (class IndexD
   GPU if the batch arrives as CUDA tensors, so SparseIndexer.index never synchronises per batch;
 * the per-term arrays are produced by ONE stable GPU radix sort of the log (ops.csr_build), bit-exact with what the
   appends would have built; `index_doc_id[t]` / `index_doc_value[t]` are numpy views into that CSR;
-* save() writes a native CSR bundle (three .npy files) next to the reference's files and, when h5py is importable,
-  also the reference's HDF5 layout (`dim`, `index_doc_id_{t}`, `index_doc_value_{t}`); the loader reads either.
+* save() writes the reference's HDF5 layout (`dim`, `index_doc_id_{t}`, `index_doc_value_{t}`; through h5py when it is
+  installed, else through the built-in writer hdf5_lite.py) and a native CSR bundle (three .npy files) next to it; the
+  loader reads either (the newer one).
 
 There is no CPU build path: finalising an index without a CUDA device raises.
 """
@@ -210,25 +211,28 @@ class IndexDictOfArray:
         off, ids, w = self.csr_host()
         print("save to disk")
         print("filename: ", self.filename)
-        for path, arr in zip(self._csr_paths(), (off, ids, w)):
-            np.save(path, arr)
         keys = np.nonzero(np.diff(off))[0]
+        # the reference's HDF5 layout (inverted_index.py:92-100): scalar `dim` + one dataset pair per non-empty posting list
+        n_dim = int(dim) if dim else len(keys)
         try:
-            import h5py  # optional: the reference's HDF5 layout (inverted_index.py:92-100)
+            import h5py
         except ImportError:
             h5py = None
-        if h5py is None:
-            import warnings
-            warnings.warn(f"h5py is not installed: {self.filename} (the reference's HDF5 layout) is NOT written; the index is "
-                          f"saved as the native CSR bundle {CSR_FILES} only, which the unmodified reference cannot load")
-            if os.path.exists(self.filename):
-                os.remove(self.filename)     # a stale HDF5 file of an older index must not outlive the new bundle
         if h5py is not None:
             with h5py.File(self.filename, "w") as f:
-                f.create_dataset("dim", data=int(dim) if dim else len(keys))
+                f.create_dataset("dim", data=n_dim)
                 for key in keys:
                     f.create_dataset("index_doc_id_{}".format(key), data=ids[off[key]:off[key + 1]])
                     f.create_dataset("index_doc_value_{}".format(key), data=w[off[key]:off[key + 1]])
+        else:   # no h5py in this environment: the same file structure from the built-in writer (hdf5_lite.py)
+            from . import hdf5_lite
+            datasets = {"dim": np.int64(n_dim)}
+            for key in keys:
+                datasets["index_doc_id_{}".format(key)] = ids[off[key]:off[key + 1]]
+                datasets["index_doc_value_{}".format(key)] = w[off[key]:off[key + 1]]
+            hdf5_lite.write_file(self.filename, datasets)
+        for path, arr in zip(self._csr_paths(), (off, ids, w)):     # written last: the loader prefers the newer artefact
+            np.save(path, arr)
         print("saving index distribution...")
         index_dist = {int(k): int(off[k + 1] - off[k]) for k in keys}
         json.dump(index_dist, open(os.path.join(self.index_path, "index_dist.json"), "w"))
@@ -294,13 +298,15 @@ def _resize_offsets(off, dim_voc):
 
 
 def _load_hdf5(filename, dim_voc):
-    """The reference loader (inverted_index.py:24-41): iterate range(dim), missing datasets -> empty lists."""
+    """The reference loader (inverted_index.py:24-41): iterate range(dim), missing datasets -> empty lists.  Read with h5py
+    when it is installed, else with the built-in reader of the file structure h5py writes by default (hdf5_lite.py)."""
     try:
         import h5py
-    except ImportError as exc:
-        raise ImportError(f"{filename} is an HDF5 index and h5py is not installed; re-save it as the native CSR bundle "
-                          f"({', '.join(CSR_FILES)}) on a machine with h5py") from exc
-    with h5py.File(filename, "r") as f:
+        opener = lambda: h5py.File(filename, "r")   # noqa: E731
+    except ImportError:
+        from . import hdf5_lite
+        opener = lambda: hdf5_lite.File(filename)   # noqa: E731
+    with opener() as f:
         dim = dim_voc if dim_voc is not None else int(f["dim"][()])
         off = np.zeros(dim + 1, dtype=np.int64)
         ids, vals = [], []
@@ -334,6 +340,16 @@ def read_index_dir(index_path, filename="array_index.h5py", dim_voc=None):
     else:
         off, ids, w = _load_hdf5(os.path.join(index_path, filename), dim_voc)
     return off.astype(np.int64), ids.astype(np.int32), w.astype(np.float32)
+
+
+def convert_hdf5_to_csr(index_path, filename="array_index.h5py", dim_voc=None):
+    """One-off converter: read the reference's HDF5 index file of `index_path` and write the native CSR bundle
+    next to it, so later loads are three np.load calls instead of 2 x dim_voc dataset reads.  Returns the bundle paths."""
+    off, ids, w = _load_hdf5(os.path.join(index_path, filename), dim_voc)
+    paths = [os.path.join(index_path, f) for f in CSR_FILES]
+    for path, arr in zip(paths, (off.astype(np.int64), ids.astype(np.int32), w.astype(np.float32))):
+        np.save(path, arr)
+    return paths
 
 
 def merge_indexes(model_name_or_path, filename="array_index.h5py", index_name="index", index_dir=None):
@@ -382,8 +398,13 @@ def merge_indexes(model_name_or_path, filename="array_index.h5py", index_name="i
 if __name__ == "__main__":
     import argparse
     parser = argparse.ArgumentParser()
-    parser.add_argument("--model_name_or_path", type=str, required=True)
+    parser.add_argument("--model_name_or_path", type=str, default=None)
     parser.add_argument("--index_name", default="index", type=str)
     parser.add_argument("--index_dir", default=None, type=str)
+    parser.add_argument("--convert_hdf5", default=None, type=str,
+                        help="(extension) index directory whose array_index.h5py is converted to the native CSR bundle; no merge")
     args = parser.parse_args()
-    merge_indexes(args.model_name_or_path, index_name=args.index_name, index_dir=args.index_dir)
+    if args.convert_hdf5:
+        print(convert_hdf5_to_csr(args.convert_hdf5))
+    else:
+        merge_indexes(args.model_name_or_path, index_name=args.index_name, index_dir=args.index_dir)

@@ -334,3 +334,24 @@ def term_search(pred, codes, k):
         _lib.check(lib.b200ret_term_search(_ptr(pred), _ptr(codes), n_queries, n_vocab, n_docs, code_len, k,
                                            _ptr(out_scores), _ptr(out_ids), _ptr(out_counts), _ptr(ws), ws_bytes, _stream()))
     return out_scores, out_ids, out_counts
+
+
+def rank_metrics(ids, counts, rel_offsets, rel_ids, mrr_cut=10, recall_cuts=(10, 100, 1000)):
+    """Per-query (reciprocal rank @mrr_cut fp32 [Q], recall @cuts fp32 [Q, len(cuts)]) of result rows `ids` [Q, k] against
+    CSR-packed relevant row labels (rel_offsets int64 [Q+1], rel_ids int64 ascending per query)."""
+    import ctypes
+    lib = _lib.load()
+    _check_cuda("ids", ids, torch.int64)
+    _check_cuda("rel_offsets", rel_offsets, torch.int64)
+    _check_cuda("rel_ids", rel_ids, torch.int64)
+    if counts is not None:
+        _check_cuda("counts", counts, torch.int32)
+    n_queries, k = ids.shape
+    cuts = (ctypes.c_int32 * max(len(recall_cuts), 1))(*[int(c) for c in recall_cuts])
+    dev = ids.device
+    with torch.cuda.device(dev):
+        rr = torch.empty(n_queries, dtype=torch.float32, device=dev)
+        recall = torch.empty((n_queries, len(recall_cuts)), dtype=torch.float32, device=dev)
+        _lib.check(lib.b200ret_rank_metrics(_ptr(ids), _ptr(counts), n_queries, k, _ptr(rel_offsets), _ptr(rel_ids), int(mrr_cut),
+                                            cuts, len(recall_cuts), _ptr(rr), _ptr(recall), _stream()))
+    return rr, recall

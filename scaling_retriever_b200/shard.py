@@ -14,8 +14,10 @@ the search kernels use — so the sharded result is identical to the 1-GPU resul
 NCCL over NVLink on GPUs, gloo on the CPU test path.  `merge_shards_allgather` is the older exchange (fp32 scores + int64 ids
 all-gathered, every rank merges every query), kept for global ids that do not fit the key's 32 bits.
 """
+import os
 from dataclasses import dataclass
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -116,3 +118,77 @@ def merge_shards(scores, ids, k, group=None, n_docs_total=None):
     ops.pack_keys(scores.contiguous(), ids.contiguous(), out=keys[:n_queries])
     merged = ops.merge_keys(exchange_keys(keys, n_queries, group), k)
     return ops.unpack_keys(gather_merged(merged, n_queries, group).contiguous(), k)
+
+
+class SharedHostRows:
+    """Result rows [n_queries, k] in HOST memory shared by the ranks of one box (a /dev/shm mapping every rank pins with
+    cudaHostRegister): after the per-slice merge each GPU copies its merged query slice over ITS OWN PCIe link straight into
+    the first worker's view of the result, instead of gathering all rows on one GPU and pushing 84 MB (6,980 x 1000 rows)
+    through a single link.  The file is unlinked as soon as every rank has mapped it."""
+    _serial = 0
+
+    def __init__(self, n_queries, k, group=None):
+        world = dist.get_world_size(group)
+        rank = dist.get_rank(group)
+        self.n_queries, self.k, self.qs = n_queries, k, query_slice(n_queries, world)
+        rows = world * self.qs
+        sizes = [rows * k * 4, rows * k * 8, rows * 4]                      # scores fp32, ids int64, counts int32
+        offsets = np.concatenate([[0], np.cumsum([(b + 255) // 256 * 256 for b in sizes])])
+        name = [None]
+        if rank == 0:
+            SharedHostRows._serial += 1
+            name[0] = f"/dev/shm/b200ret_{os.getpid()}_{SharedHostRows._serial}"
+            with open(name[0], "wb") as f:
+                f.truncate(int(offsets[-1]))
+        dist.broadcast_object_list(name, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        self._raw = torch.from_file(name[0], shared=True, size=int(offsets[-1]), dtype=torch.uint8)
+        self._registered = False
+        if torch.cuda.is_available():
+            err = torch.cuda.cudart().cudaHostRegister(self._raw.data_ptr(), self._raw.numel(), 0)
+            self._registered = int(err) == 0
+        dist.barrier(group)
+        if rank == 0:
+            os.unlink(name[0])
+        self.scores = self._raw[offsets[0]:offsets[0] + sizes[0]].view(torch.float32).view(rows, k)
+        self.ids = self._raw[offsets[1]:offsets[1] + sizes[1]].view(torch.int64).view(rows, k)
+        self.counts = self._raw[offsets[2]:offsets[2] + sizes[2]].view(torch.int32)
+
+    def slice_views(self, rank):
+        a, b = rank * self.qs, (rank + 1) * self.qs
+        return self.scores[a:b], self.ids[a:b], self.counts[a:b]
+
+    def result(self):
+        q = self.n_queries
+        return self.scores[:q].numpy(), self.ids[:q].numpy(), self.counts[:q].numpy()
+
+    def __del__(self):
+        try:
+            if self._registered:
+                torch.cuda.cudart().cudaHostUnregister(self._raw.data_ptr())
+        except Exception:
+            pass
+
+
+def merge_shards_to_first_host(scores, ids, k, host, group=None):
+    """Sharded search, result wanted on the FIRST worker's host only (the rank that writes run.json): packed-key all-to-all,
+    per-slice merge, then every rank copies its merged slice into the shared host rows (`host`: SharedHostRows) over its own
+    PCIe link.  Returns (scores, ids, counts) numpy views on the first worker, (None, None, None) elsewhere; bytes copied by
+    this rank are returned as the 4th value."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n_queries = scores.shape[0]
+    qs = host.qs
+    keys = torch.empty((world * qs, k), dtype=torch.int64, device=scores.device)
+    keys[n_queries:].zero_()
+    ops.pack_keys(scores.contiguous(), ids.contiguous(), out=keys[:n_queries])
+    merged = ops.merge_keys(exchange_keys(keys, n_queries, group), k)
+    m_scores, m_ids, m_counts = ops.unpack_keys(merged, k)
+    h_scores, h_ids, h_counts = host.slice_views(rank)
+    h_scores.copy_(m_scores, non_blocking=True)
+    h_ids.copy_(m_ids, non_blocking=True)
+    h_counts.copy_(m_counts, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    dist.barrier(group)                      # every slice has landed in the shared rows
+    nbytes = m_scores.numel() * 4 + m_ids.numel() * 8 + m_counts.numel() * 4
+    if rank == 0:
+        return (*host.result(), nbytes)
+    return None, None, None, nbytes

@@ -38,8 +38,13 @@ def main():
     part = ops.SparseDeviceIndex.from_coo((rows[keep] - lo).contiguous(), cols[keep].contiguous(), vals[keep].contiguous(),
                                           n_terms, hi - lo)
     s, i, c = ops.sparse_search(part, q_off, q_t, q_w, k, 0.0, doc_id_base=lo)
-    s, i, c = shard.merge_shards(s, i, k)
+    loc_s, loc_i = s, i
+    s, i, c = shard.merge_shards(loc_s, loc_i, k, n_docs_total=n_docs)      # packed-key all-to-all + per-slice merge + all-gather
     assert torch.equal(i, ref_i) and torch.equal(c, ref_c) and torch.equal(s.view(torch.int32), ref_s.view(torch.int32)), "sparse ops"
+    s, i, c = shard.merge_shards_allgather(loc_s, loc_i, k)                  # the 64-bit-id exchange gives the same rows
+    assert torch.equal(i, ref_i) and torch.equal(c, ref_c) and torch.equal(s.view(torch.int32), ref_s.view(torch.int32)), "sparse allgather"
+    s, i, c = shard.merge_shards(loc_s, loc_i, k, n_docs_total=1 << 33)      # ids beyond a key's 32 bits take that exchange
+    assert torch.equal(i, ref_i), "sparse 64-bit fallback"
 
     # ---- sparse: class API (SparseRetrieval shards by itself under a process group) ------------------------------------
     index = IndexDictOfArray(index_path=None, dim_voc=n_terms, device=dev)
@@ -49,8 +54,18 @@ def main():
     assert retr.doc_id_base == lo and retr.device_index.n_docs == hi - lo
     h = retr.search_arrays(q_off.cpu().numpy(), q_t.cpu().numpy(), q_w.cpu().numpy(), k, 0.0)
     assert np.array_equal(h[1], ref_i.cpu().numpy()) and np.array_equal(h[0].view(np.uint32), ref_s.cpu().numpy().view(np.uint32))
+    for _ in range(2):     # host_ranks="first": every rank copies its merged query slice into host rows shared with rank 0
+        h1 = retr.search_arrays(q_off.cpu().numpy(), q_t.cpu().numpy(), q_w.cpu().numpy(), k, 0.0, host_ranks="first")
+        if rank == 0:
+            assert np.array_equal(h1[1], ref_i.cpu().numpy()) and np.array_equal(h1[0].view(np.uint32), ref_s.cpu().numpy().view(np.uint32))
+            assert np.array_equal(h1[2], ref_c.cpu().numpy())
+        else:
+            assert h1 == (None, None, None)
     res, _ = retr._sparse_retrieve_multithreaded(synth.queries_to_vecs(q_off, q_t, q_w), list(range(n_queries)), 0.0, k)
-    assert res["3"][f"D{int(ref_i[3, 0])}"] == float(ref_s[3, 0])
+    if rank == 0:          # the run lives on the first worker (the rank that writes run.json); the others get an empty run
+        assert res["3"][f"D{int(ref_i[3, 0])}"] == float(ref_s[3, 0]) and len(res) == int((ref_c > 0).sum())
+    else:
+        assert len(res) == 0
 
     # ---- dense ---------------------------------------------------------------------------------------------------------
     nd, dim, nq, kd = 30007, 256, 70, 200
@@ -60,7 +75,7 @@ def main():
     ref_s, ref_i, _ = ops.dense_search(docs, q16, kd)
     lo, hi = shard.ShardPlan(nd, world).bounds(rank)
     s, i, _ = ops.dense_search(docs[lo:hi].contiguous(), q16, kd, doc_id_base=lo)
-    s, i, _ = shard.merge_shards(s, i, kd)
+    s, i, _ = shard.merge_shards(s, i, kd, n_docs_total=nd)
     assert torch.equal(i, ref_i) and torch.equal(s.view(torch.int32), ref_s.view(torch.int32)), "dense ops"
     flat = DenseFlatIndexer(device=dev)
     flat.init_index(dim)
@@ -68,6 +83,11 @@ def main():
     assert flat.index.shape[0] == hi - lo
     top_ids, top_scores = flat.search_knn(queries.cpu().numpy(), kd)
     assert top_ids[5][0] == f"P{int(ref_i[5, 0])}" and np.array_equal(top_scores, ref_s.cpu().numpy())
+    d1 = flat.search_arrays(queries.cpu().numpy(), kd, host_ranks="first")
+    if rank == 0:
+        assert np.array_equal(d1[1], ref_i.cpu().numpy()) and np.array_equal(d1[0], ref_s.cpu().numpy())
+    else:
+        assert d1 == (None, None)
 
     dist.barrier()
     if rank == 0:

@@ -43,3 +43,25 @@ def test_reference_arm_nonzero_rank_is_silent():
 def test_b200_arm_fails_loudly_without_cuda():
     proc = run_bench(["--steps", "1", "--warmup", "0", "--n-docs", "1000", "--n-queries", "4"])
     assert proc.returncode != 0 and "CUDA" in (proc.stderr + proc.stdout)
+
+
+def test_reference_arm_default_line_covers_sparse_and_dense_with_all_cores_under_torchrun_env():
+    """Default workload = both halves of the metric in ONE line (dense as a sub-record); the thread count is the box's cores even
+    with the OMP_NUM_THREADS=1 that torch.distributed.run exports to every rank; `config` is built from
+    the command line only, so the B200 arm of the same command prints the identical dict (`same_config`)."""
+    args = ["--impl", "reference", "--steps", "1", "--warmup", "0", "--n-docs", "3000", "--n-queries", "16"]
+    proc = run_bench(args, env={"OMP_NUM_THREADS": "1", "RANK": "0", "WORLD_SIZE": "1", "LOCAL_RANK": "0"})
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    lines = [l for l in proc.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    cores = len(os.sched_getaffinity(0))
+    assert d["cpu_baseline"]["cores"] == cores
+    assert d["dense"]["impl"] == "reference" and d["dense"]["cpu_baseline"]["cores"] == cores and d["dense"]["value"] > 0
+    assert "dense_4096" not in d
+    sys.path.insert(0, ROOT)
+    import argparse
+    import bench
+    ns = argparse.Namespace(n_docs=3000, n_queries=16, gpus=1, workload="both", dim=2048)
+    assert d["config"] == bench.sparse_config(ns) and d["dense"]["config"] == bench.dense_config(ns, 2048)
+    assert bench.dense_dims(argparse.Namespace(workload="both", gpus=8, dim=2048)) == [2048, 4096]

@@ -80,6 +80,21 @@ def _worker(rank, world, port, tmp):
     u_scores, u_ids, u_counts = unpack_keys_reference(got)
     ok = ok and np.array_equal(u_ids, full[1]) and np.array_equal(u_scores.view(np.uint32), full[0].view(np.uint32)) \
         and np.array_equal(u_counts, full[2])
+
+    # shared host rows (shard.SharedHostRows): every rank writes its merged query slice, the first worker reads all of them
+    host = shard.SharedHostRows(nq, k)
+    a, b = rank * qs, min(nq, (rank + 1) * qs)
+    hs, hi, hc = host.slice_views(rank)
+    hs[:b - a].copy_(torch.as_tensor(u_scores[a:b]))
+    hi[:b - a].copy_(torch.as_tensor(u_ids[a:b]))
+    hc[:b - a].copy_(torch.as_tensor(u_counts[a:b]))
+    dist.barrier()
+    if rank == 0:
+        r_s, r_i, r_c = host.result()
+        ok = ok and np.array_equal(r_i, full[1]) and np.array_equal(r_s.view(np.uint32), full[0].view(np.uint32)) \
+            and np.array_equal(r_c, full[2])
+        ok = ok and not any(n.startswith("b200ret_") for n in os.listdir("/dev/shm"))      # the mapping's file is already unlinked
+    dist.barrier()
     np.save(os.path.join(tmp, f"ok_{rank}.npy"), np.array([ok]))
     dist.barrier()
     dist.destroy_process_group()

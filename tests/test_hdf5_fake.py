@@ -123,15 +123,35 @@ def test_hdf5_save_and_load_paths_with_fake_h5py(fake_h5py, golden, tmp_path):
     assert np.array_equal(r_off, off) and np.array_equal(r_ids, ids)
 
 
-def test_missing_h5py_is_loud(golden, tmp_path, monkeypatch):
-    from scaling_retriever_b200 import inverted_index as inv
+def test_without_h5py_the_builtin_hdf5_reader_and_writer_are_used(golden, tmp_path, monkeypatch):
+    """No h5py (this image): save() writes array_index.h5py with hdf5_lite.write_file, and the reference's loader logic reads it
+    back through hdf5_lite.File — same datasets, dtypes and `dim` semantics as with h5py."""
+    from scaling_retriever_b200 import hdf5_lite, inverted_index as inv
     monkeypatch.setitem(sys.modules, "h5py", None)                                # import h5py -> ImportError
-    open(tmp_path / "array_index.h5py", "wb").write(b"\x89HDF\r\n\x1a\n")
-    with pytest.raises(ImportError, match="h5py is not installed"):
-        inv.read_index_dir(str(tmp_path), "array_index.h5py", 10)
-    off, ids, vals = golden["A_offsets"], golden["A_ids"], golden["A_vals"]
-    index = inv.IndexDictOfArray(str(tmp_path), force_new=True, dim_voc=len(off) - 1)
+    off, ids, vals = golden["C_offsets"], golden["C_ids"], golden["C_vals"]
+    n_terms = len(off) - 1
+    index = inv.IndexDictOfArray(str(tmp_path), force_new=True, dim_voc=n_terms)
     index._set_csr_host(off.astype(np.int64), ids.astype(np.int32), vals.astype(np.float32))
-    with pytest.warns(UserWarning, match="NOT written"):
-        index.save()
-    assert not os.path.exists(tmp_path / "array_index.h5py")                      # the stale HDF5 file is removed, not kept
+    index.n = int(ids.max()) + 1
+    index.save()
+    h5 = str(tmp_path / "array_index.h5py")
+    with open(h5, "rb") as f:
+        assert f.read(8) == b"\x89HDF\r\n\x1a\n"
+    fake = types.ModuleType("h5py")
+    fake.File = lambda name, mode="r": hdf5_lite.File(name)
+    monkeypatch.setitem(sys.modules, "h5py", fake)                                # the reference's loader, over the real file
+    ref_ids, ref_vals = reference_loader(h5, n_terms)
+    monkeypatch.setitem(sys.modules, "h5py", None)
+    for t in range(n_terms):
+        assert np.array_equal(ref_ids[t], ids[off[t]:off[t + 1]]) and np.array_equal(ref_vals[t], vals[off[t]:off[t + 1]])
+    with hdf5_lite.File(h5) as f:
+        assert int(f["dim"][()]) == int(np.count_nonzero(np.diff(off))) and f["dim"].dtype == np.int64
+        assert f["index_doc_id_0"].dtype == np.int32 and f["index_doc_value_0"].dtype == np.float32
+    for p in [os.path.join(str(tmp_path), f) for f in inv.CSR_FILES]:             # HDF5-only directory (what the reference writes)
+        os.remove(p)
+    l_off, l_ids, l_vals = inv.read_index_dir(str(tmp_path), "array_index.h5py", n_terms)
+    assert np.array_equal(l_off, off) and np.array_equal(l_ids, ids) and np.array_equal(l_vals.view(np.uint32), vals.view(np.uint32))
+    assert not any(os.path.exists(os.path.join(str(tmp_path), f)) for f in inv.CSR_FILES)
+    inv.convert_hdf5_to_csr(str(tmp_path), dim_voc=n_terms)                       # HDF5 -> CSR bundle converter
+    c_off, c_ids, c_vals = (np.load(os.path.join(str(tmp_path), f)) for f in inv.CSR_FILES)
+    assert np.array_equal(c_off, off) and np.array_equal(c_ids, ids) and np.array_equal(c_vals.view(np.uint32), vals.view(np.uint32))

@@ -113,3 +113,13 @@ def test_select_topk_static_keeps_reference_semantics():
     assert len(sel) == 3 and 5 in sel and np.all(sc >= 2)
     sel, sc = SparseRetrieval.select_topk(idx, neg, 10)
     assert np.array_equal(sel, idx) and np.array_equal(sc, -neg)
+
+
+def test_metrics_oracle_hand_example():
+    """oracle/metrics_oracle.py (restatement of utils/metrics.py:13-42 + trec_eval definitions) on a hand-computed case."""
+    from oracle import metrics_oracle as m
+    run = {"a": {"4": 4.0, "2": 3.0, "9": 2.0, "1": 1.0}, "b": {"7": 9.0, "8": 8.0, "3": 7.0, "0": 6.0}}
+    qrel = {"a": {"9": 1, "1": 1, "5": 1}, "b": {"6": 1}, "c": {"1": 1}}
+    assert m.mrr_k(run, qrel, 10) == (1 / 3 + 0) / 2 and m.mrr_k(run, qrel, 2) == 0.0
+    assert m.recall_k(run, qrel, 3) == (1 / 3) / 2 and m.recall_k(run, qrel, 1000) == (2 / 3) / 2
+    assert m.truncate_run(run, 2)["a"] == {"4": 4.0, "2": 3.0}
