@@ -36,13 +36,13 @@
 namespace b200ret {
 
 #ifndef B200RET_SCORE_WARPS     // kernel shape (tuning knobs): warps per CTA, docs per warp tile, blocks in round 0
-#define B200RET_SCORE_WARPS 16
-#define B200RET_BLOCK_DOCS 3328
+#define B200RET_SCORE_WARPS 15
+#define B200RET_BLOCK_DOCS 3584
 #define B200RET_ROUND0_BLOCKS 2
 #endif
 constexpr int ROUND0_BLOCKS = B200RET_ROUND0_BLOCKS;   // first round / safe-schedule round size, in doc blocks
 #ifndef B200RET_LDNC           // posting-load flavour (tuning knob)
-#define B200RET_LDNC "ld.global.nc"
+#define B200RET_LDNC "ld.global.nc.L2::256B"
 #endif
 #ifndef B200RET_BATCH_STEPS     // steps per register batch (two batches, double-buffered); 2 and 3 measure equal
 #define B200RET_BATCH_STEPS 2
@@ -55,6 +55,9 @@ constexpr int STEP_ROWS = 4;                     // rows (of 32 postings) fetche
 #define B200RET_DESC_MODE 1
 #endif
 constexpr int DESC_MODE = B200RET_DESC_MODE;
+#if defined(B200RET_ADV_MODE) && B200RET_ADV_MODE == 2 && B200RET_DESC_MODE != 1
+#error "B200RET_ADV_MODE 2 forms its addresses for the DESC_MODE 1 layout"
+#endif
 // Row-liveness predicates of a step (tuning knob): 0 = four unsigned compares of rel + 32 r against len (3 adds + 4 setp),
 // 1 = one subtraction + compares against immediates (1 sub + 4 setp)
 #ifndef B200RET_PRED_MODE
@@ -62,8 +65,11 @@ constexpr int DESC_MODE = B200RET_DESC_MODE;
 #endif
 // Tile sweep (tuning knob): 1 = blocks that lie entirely inside the collection skip the per-document bound checks;
 // 2 = additionally clear unconditionally and branch only for lanes with a hit
-#ifndef B200RET_ADV_MODE        // cursor advance (tuning knob): 1 = fused predicate compares, bit-reversed pending mask
-#define B200RET_ADV_MODE 1
+#ifndef B200RET_ADV_MODE        // cursor advance (tuning knob): 1 = fused predicate compares, bit-reversed pending mask;
+#define B200RET_ADV_MODE 1      // 2 = additionally addresses formed from the highest-set-bit index (needs DESC_MODE 1)
+#endif
+#ifndef B200RET_ADDR32          // 1 = posting row address from a 32-bit position (one IMAD.WIDE) instead of 64-bit pointer arithmetic
+#define B200RET_ADDR32 0
 #endif
 #ifndef B200RET_SWEEP_FAST
 #define B200RET_SWEEP_FAST 2
@@ -74,7 +80,7 @@ constexpr int DESC_BUF_WORDS = DESC_MODE >= 2 ? 128 : 96;     // one descriptor 
 
 // Kernel shape: one CTA of WARPS warps per SM, BD docs per warp-private score tile (BD * 4 bytes of shared memory).
 constexpr int SCORE_WARPS = B200RET_SCORE_WARPS;
-constexpr int BLOCK_DOCS = B200RET_BLOCK_DOCS;   // default: 16 warps x (13.5 KB scores + 384 B slice descriptors) = 222 KB of 227 KB
+constexpr int BLOCK_DOCS = B200RET_BLOCK_DOCS;   // default: 15 warps x (14 KB scores + 1088 B control area) = 226 KB of 227 KB
 constexpr int SCORE_THREADS = SCORE_WARPS * 32;
 // Per-warp control area in shared memory (uint32 words): two descriptor buffers (beg[32], end[32], query weight[32]) used
 // alternately by consecutive term groups, the staged term ids / weights of the group after the next, and the cold,
@@ -392,11 +398,17 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
             "clz.b32 j, t;\n\t"                             // index of the lowest pending slice
             "add.u32 t, %4, -1;\n\t"
             "@take and.b32 %4, %4, t;\n\t"
-#else       // `pending` is kept BIT-REVERSED (slice j <-> bit 31 - j): the next slice is the count of leading zeros
+#elif B200RET_ADV_MODE == 1   // `pending` is kept BIT-REVERSED (slice j <-> bit 31 - j): the next slice is the count of leading zeros
             "setp.ne.and.u32 take, %4, 0, adv;\n\t"
             "setp.eq.and.u32 dead, %4, 0, adv;\n\t"         // exhausted and nothing pending: empty step
             "clz.b32 j, %4;\n\t"                            // index of the lowest pending slice (32 when none: loads predicated off)
             "shr.u32 t, 0x80000000, j;\n\t"
+            "@take xor.b32 %4, %4, t;\n\t"
+#else       // mode 2: bit-reversed `pending`, next slice j = 31 - (highest set bit f); addresses are formed from f directly
+            "setp.ne.and.u32 take, %4, 0, adv;\n\t"
+            "setp.eq.and.u32 dead, %4, 0, adv;\n\t"
+            "bfind.u32 j, %4;\n\t"                          // f (0xffffffff when none: loads predicated off, shift gives 0)
+            "shl.b32 t, 1, j;\n\t"
             "@take xor.b32 %4, %4, t;\n\t"
 #endif
 #if B200RET_DESC_MODE == 0
@@ -405,6 +417,11 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
             "@take ld.shared.u32 %1, [a];\n\t"              // c_beg
             "@take ld.shared.u32 %2, [a + 128];\n\t"        // c_end
             "@take ld.shared.f32 %3, [a + 256];\n\t"        // c_qw
+#elif B200RET_DESC_MODE == 1 && B200RET_ADV_MODE == 2
+            "mad.lo.s32 a, j, -8, %6;\n\t"                  // desc + 8 * (31 - f)
+            "@take ld.shared.v2.u32 {%1, %2}, [a + 248];\n\t"   // {c_beg, c_end}
+            "mad.lo.s32 a, j, -4, %6;\n\t"
+            "@take ld.shared.f32 %3, [a + 380];\n\t"        // c_qw at desc + 256 + 4 * (31 - f)
 #elif B200RET_DESC_MODE == 1
             "shl.b32 a, j, 3;\n\t"
             "add.u32 a, a, %6;\n\t"
@@ -425,8 +442,14 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
             : "r"(desc_s)
             : "memory");
         qw = c_qw;
+#if B200RET_ADDR32
+        const unsigned pos = c_row + lane;          // < nnz < 2^32 (csr_build rejects larger indexes): 32-bit sum, one widening multiply-add
+        rel = pos - c_beg;
+        row0 = p.postings + pos;
+#else
         rel = c_row + lane - c_beg;
         row0 = g_post + c_row;     // one 64-bit address per step; rows are 256 bytes apart (immediates)
+#endif
         c_row += 32u * R;
     };
     // Fetch one step into ring registers.  The cold path (once per term group) installs the next group's descriptors,

@@ -12,37 +12,62 @@
 
 namespace b200ret {
 
-// MSB-first 8-bit radix select: returns the k-th largest key (1 <= k <= n) of keys[0..n).
+// MSB-first radix select with 8-bit digits: returns the k-th largest key (1 <= k <= n) of keys[0..n).
 // `hist` is 256 shared counters, `bcast` three shared u64 slots.  All threads of the block call it.
-// Early exit: as soon as the bucket that holds the k-th key contains exactly as many keys as are still needed, every key
-// of that bucket is selected and the k-th key is simply the bucket's minimum (one min pass instead of the remaining digit
-// passes; with fp32 scores in the high half this happens after 3-4 of the 8 passes).
+// * Common prefix first: one OR-reduction of key ^ keys[0] finds the highest bit in which the keys differ, and the digit
+//   windows start THERE instead of at bit 63.  Candidate scores sit in a narrow range (same sign and exponent, often the same
+//   leading mantissa bits), so byte-aligned passes from the top spent one or two whole passes putting every key into ONE
+//   histogram bin — thousands of serialised shared-memory atomics on the same address per query (the select launches were
+//   0.2-0.3 ms each, a per-rank fixed cost that does not shrink with the shard).
+// * Early exit: as soon as the bucket that holds the k-th key contains exactly as many keys as are still needed, every key of
+//   that bucket is selected and the k-th key is simply the bucket's minimum (one min pass instead of the remaining passes).
 __device__ inline uint64_t block_radix_select_kth(const uint64_t* keys, int n, int k, uint32_t* hist,
                                                   uint64_t* bcast) {
-    uint64_t prefix = 0, mask = 0;
+    // ---- highest differing bit ----
+    if (threadIdx.x == 0) bcast[0] = 0;
+    __syncthreads();
+    {
+        const uint64_t k0 = keys[0];
+        unsigned long long x = 0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) x |= keys[i] ^ k0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) x |= __shfl_xor_sync(0xffffffffu, x, off);
+        if ((threadIdx.x & 31) == 0 && x) atomicOr(reinterpret_cast<unsigned long long*>(bcast), x);
+    }
+    __syncthreads();
+    const uint64_t diff = bcast[0];
+    __syncthreads();
+    if (diff == 0) return keys[0];                                      // all keys equal (n == 1, keys are unique otherwise)
+    int hi = 63 - __clzll(static_cast<long long>(diff));                // block-uniform
+    uint64_t mask = (hi == 63) ? 0ull : ~((2ull << hi) - 1ull);         // bits above the first differing one: common to all keys
+    uint64_t prefix = keys[0] & mask;
     int remaining = k;
-    for (int shift = 56; shift >= 0; shift -= 8) {
-        if (shift < 56 && static_cast<int>(bcast[2]) == remaining) {   // bucket size == keys still needed (block-uniform)
+    bool first = true;
+    while (hi >= 0) {
+        const int lo = max(0, hi - 7);
+        const uint32_t dmask = (1u << (hi - lo + 1)) - 1u;
+        if (!first && static_cast<int>(bcast[2]) == remaining) {        // bucket size == keys still needed (block-uniform)
             if (threadIdx.x == 0) bcast[0] = ~0ull;
             __syncthreads();
-            unsigned long long lo = ~0ull;
+            unsigned long long lo_key = ~0ull;
             for (int i = threadIdx.x; i < n; i += blockDim.x) {
                 const uint64_t key = keys[i];
-                if ((key & mask) == prefix) lo = min(lo, static_cast<unsigned long long>(key));
+                if ((key & mask) == prefix) lo_key = min(lo_key, static_cast<unsigned long long>(key));
             }
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, off));
-            if ((threadIdx.x & 31) == 0 && lo != ~0ull) atomicMin(reinterpret_cast<unsigned long long*>(bcast), lo);
+            for (int off = 16; off > 0; off >>= 1) lo_key = min(lo_key, __shfl_xor_sync(0xffffffffu, lo_key, off));
+            if ((threadIdx.x & 31) == 0 && lo_key != ~0ull) atomicMin(reinterpret_cast<unsigned long long*>(bcast), lo_key);
             __syncthreads();
             const uint64_t kth = bcast[0];
             __syncthreads();
             return kth;
         }
+        first = false;
         for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
         __syncthreads();
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             const uint64_t key = keys[i];
-            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xff], 1u);
+            if ((key & mask) == prefix) atomicAdd(&hist[static_cast<uint32_t>(key >> lo) & dmask], 1u);
         }
         __syncthreads();
         if (threadIdx.x < 32) {
@@ -77,9 +102,10 @@ __device__ inline uint64_t block_radix_select_kth(const uint64_t* keys, int n, i
         __syncthreads();
         const uint64_t digit = bcast[0];
         remaining = static_cast<int>(bcast[1]);
-        prefix |= digit << shift;
-        mask |= 0xffull << shift;
+        prefix |= digit << lo;
+        mask |= static_cast<uint64_t>(dmask) << lo;
         __syncthreads();
+        hi = lo - 1;
     }
     return prefix;
 }

@@ -23,7 +23,7 @@ import torch
 from tqdm import tqdm
 
 from . import ops, shard
-from .inverted_index import IndexDictOfArray
+from .inverted_index import MAX_SHARD_POSTINGS, IndexDictOfArray
 from .results import ExternalIds, IdRows, LazyRun
 from .utils import is_first_worker, obtain_doc_vec_dir_files, rank as _rank, supports_bfloat16, to_list, world_size as _world_size
 
@@ -561,8 +561,9 @@ class SparseRetrieval:
             self.sparse_index.device = self._cuda
             self.shard_plan = shard.ShardPlan(self.size_collection, _world_size())
             lo, hi = self.shard_plan.bounds(_rank()) if self.shard_plan.world_size > 1 else (0, self.size_collection)
-            self.device_index = self.sparse_index.device_index(lo, hi)
-            self.doc_id_base = lo
+            # one search-side index normally; several consecutive doc ranges when this rank's share holds >= 2^32 postings
+            self.device_shards = self.sparse_index.device_shards(lo, hi, kwargs.get("max_shard_postings") or MAX_SHARD_POSTINGS)
+            self.device_index, self.doc_id_base = self.device_shards[0]
 
         self.out_dir = os.path.join(config["out_dir"], dataset_name) if (dataset_name is not None and not is_beir) \
             else config["out_dir"]
@@ -605,8 +606,7 @@ class SparseRetrieval:
             d_off = self._stage_in("q_off", q_offsets, torch.int32)
             d_terms = self._stage_in("q_terms", q_terms, torch.int32)
             d_w = self._stage_in("q_w", q_weights, torch.float32)
-            scores, ids, counts = ops.sparse_search(self.device_index, d_off, d_terms, d_w, int(topk), float(threshold),
-                                                    doc_id_base=self.doc_id_base)
+            scores, ids, counts = self._search_local(d_off, d_terms, d_w, int(topk), float(threshold))
             if self.shard_plan.world_size > 1:
                 if host_ranks == "first" and self.size_collection < shard.KEY_ID_LIMIT:
                     # every GPU copies its merged query slice into host rows shared with the first worker (own PCIe link each)
@@ -619,6 +619,13 @@ class SparseRetrieval:
             out = [self._stage_out(name, t) for name, t in (("scores", scores), ("ids", ids), ("counts", counts))]
             torch.cuda.current_stream().synchronize()
             return tuple(o.numpy() for o in out)
+
+    def _search_local(self, d_off, d_terms, d_w, topk, threshold):
+        """This rank's rows: one kernel pass per local doc-range index, merged when there are several."""
+        parts = [ops.sparse_search(index, d_off, d_terms, d_w, topk, threshold, doc_id_base=base) for index, base in self.device_shards]
+        if len(parts) == 1:
+            return parts[0]
+        return ops.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), topk)
 
     def _shared_rows(self, n_queries, k):
         key = (n_queries, k)
@@ -643,6 +650,7 @@ class SparseRetrieval:
         self.sparse_index = None
         self.device_index = device_index
         self.doc_id_base = doc_id_base
+        self.device_shards = [(device_index, doc_id_base)]
         self.size_collection = device_index.n_docs if size_collection is None else size_collection
         self.shard_plan = shard.ShardPlan(self.size_collection, _world_size())
         self.doc_ids = doc_ids if doc_ids is not None else range(self.size_collection)

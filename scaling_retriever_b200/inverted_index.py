@@ -25,6 +25,7 @@ import torch
 from . import ops
 
 CSR_FILES = ("csr_term_offsets.npy", "csr_doc_ids.npy", "csr_weights.npy")
+MAX_SHARD_POSTINGS = (1 << 32) - (1 << 20)     # the kernels address postings with 32-bit positions (csr_build.cu, skip table)
 
 
 class _TermArrays(Mapping):
@@ -238,6 +239,21 @@ class IndexDictOfArray:
         json.dump(index_dist, open(os.path.join(self.index_path, "index_dist.json"), "w"))
 
     # ---- search-side view -----------------------------------------------------------------------------------
+    def device_shards(self, doc_lo=0, doc_hi=None, max_postings=MAX_SHARD_POSTINGS):
+        """[(SparseDeviceIndex, first doc row)] covering doc rows [doc_lo, doc_hi): ONE entry normally; a range that holds more
+        postings than the kernels' 32-bit positions address (>= 2^32, e.g. 20 M docs x 200 terms on one GPU) is cut into
+        consecutive doc ranges that are searched one after the other and merged (SparseRetrieval.search_arrays)."""
+        doc_hi = int(self.n) if doc_hi is None else doc_hi
+        nnz = len(self._csr_host[1]) if self._csr_host is not None else (self._csr_dev[1].numel() if self._csr_dev is not None else
+                                                                          sum(r.numel() for r, _, _ in self._log))
+        if nnz <= max_postings:
+            return [(self.device_index(doc_lo, doc_hi), doc_lo)]
+        if self._csr_host is None:
+            raise NotImplementedError(f"an index of {nnz} postings built in memory exceeds the 32-bit posting positions of one "
+                                      "CSR build; save and load it (the loader cuts it into doc ranges), or index under torchrun")
+        off, ids, _ = self._csr_host
+        return [(self.device_index(a, b), a) for a, b in split_doc_range(off, ids, doc_lo, doc_hi, max_postings)]
+
     def device_index(self, doc_lo=0, doc_hi=None):
         """Search-side index on the GPU for doc rows [doc_lo, doc_hi) (default: all; row ids become local to the range):
         doc-sorted CSR + doc-block skip table, slices in bank order.  The canonical CSR of this object is not modified."""
@@ -267,6 +283,28 @@ class IndexDictOfArray:
         cols = torch.repeat_interleave(torch.arange(off.numel() - 1, dtype=torch.int32, device=off.device), counts,
                                        output_size=ids.numel())
         return ops.SparseDeviceIndex.from_coo(ids, cols, w, off.numel() - 1, n_docs)
+
+
+def split_doc_range(off, ids, lo, hi, max_postings):
+    """Cut doc rows [lo, hi) into consecutive ranges holding <= max_postings postings each (host CSR; one bincount pass)."""
+    if hi <= lo:
+        return [(lo, hi)]
+    per_doc = np.zeros(hi - lo, dtype=np.int64)
+    step = 1 << 26
+    for a in range(0, len(ids), step):
+        seg = ids[a:a + step]
+        seg = seg[(seg >= lo) & (seg < hi)] - lo
+        per_doc += np.bincount(seg, minlength=hi - lo)
+    csum = np.cumsum(per_doc)
+    bounds, start, base = [], lo, 0
+    while start < hi:
+        end = lo + int(np.searchsorted(csum, base + max_postings, side="right"))
+        end = max(end, start + 1)
+        end = min(end, hi)
+        bounds.append((start, end))
+        base = int(csum[end - lo - 1])
+        start = end
+    return bounds
 
 
 def shard_csr_host(off, ids, w, lo, hi, terms_per_chunk=2048):

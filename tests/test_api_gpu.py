@@ -445,3 +445,36 @@ def test_out_of_range_terms_are_rejected_before_the_kernels(cuda):
     index.add_batch_document(np.array([0, 1]), np.array([3, 10]), np.array([1.0, 2.0], dtype=np.float32), n_docs=2)
     with pytest.raises(ValueError, match="term ids must be in"):
         index.finalize()
+
+
+def test_index_beyond_the_32_bit_position_limit_is_searched_in_doc_ranges(golden, golden_run, cuda, tmp_path):
+    """the kernels address postings with 32-bit positions, so an index with >= 2^32 postings (20 M docs on
+    one GPU) is cut into consecutive doc ranges that are searched one after the other and merged.  Exercised here by lowering
+    the per-range posting budget (`max_shard_postings`): the run must equal the single-index run of the reference golden."""
+    off, ids, vals = golden["C_offsets"], golden["C_ids"], golden["C_vals"]
+    n_docs, n_terms = int(golden["C_n_docs"]), int(golden["C_n_terms"])
+    built = IndexDictOfArray(str(tmp_path), force_new=True, dim_voc=n_terms)
+    built.add_batch_document(ids, np.repeat(np.arange(n_terms), np.diff(off)), vals, n_docs=n_docs)
+    built.save()
+    ext_ids = [f"D{7 * i}" for i in range(n_docs)]
+    with open(tmp_path / "doc_ids.pkl", "wb") as f:
+        pickle.dump({i: ext_ids[i] for i in range(n_docs)}, f)
+    out_dir = str(tmp_path / "out")
+    os.makedirs(out_dir)
+    budget = len(ids) // 5 + 1
+    retr = SparseRetrieval(torch.nn.Linear(1, 1), {"index_dir": str(tmp_path), "out_dir": out_dir}, n_terms, 0, max_shard_postings=budget)
+    assert len(retr.device_shards) >= 5 and retr.device_shards[0][1] == 0
+    assert sum(index.nnz for index, _ in retr.device_shards) == len(ids)
+    assert all(index.nnz <= budget for index, _ in retr.device_shards)
+    one = SparseRetrieval(torch.nn.Linear(1, 1), {"index_dir": str(tmp_path), "out_dir": out_dir}, n_terms, 0)
+    assert len(one.device_shards) == 1
+    q_off, q_t, q_w = golden["C_q_offsets"], golden["C_q_terms"], golden["C_q_weights"]
+    a = retr.search_arrays(q_off, q_t, q_w, golden_run["topk"], golden_run["threshold"])
+    a = tuple(np.array(x) for x in a)
+    b = one.search_arrays(q_off, q_t, q_w, golden_run["topk"], golden_run["threshold"])
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32)) and np.array_equal(a[2], b[2])
+    vecs = [(q_t[q_off[i]:q_off[i + 1]], q_w[q_off[i]:q_off[i + 1]]) for i in range(len(q_off) - 1)]
+    res, _ = retr._sparse_retrieve_multithreaded(vecs, golden_run["qids"], golden_run["threshold"], golden_run["topk"])
+    assert set(res.keys()) == set(golden_run["res"].keys())
+    for qid, ref_docs in golden_run["res"].items():
+        assert sorted(res[qid].values(), reverse=True) == sorted(ref_docs.values(), reverse=True)

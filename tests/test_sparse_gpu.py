@@ -235,10 +235,11 @@ def test_search_ragged_query_mix_exercises_pipeline_control(cuda):
     """Runs of empty queries, one-term queries and 150-term queries (five term groups) over a corpus whose postings sit in a
     few doc blocks only: items without any posting directly behind each other, groups with only empty slices, warps that
     get no item at all — every control path of the score kernel's never-draining load pipeline, vs the C oracle."""
-    n_docs, n_terms = 3328 * 9 + 17, 600
+    bd = ops.block_docs()
+    n_docs, n_terms = bd * 9 + 17, 600
     g = torch.Generator(device="cpu").manual_seed(77)
     rows, cols, vals = synth.gen_sparse_docs(n_docs, n_terms=n_terms, mean_nnz=30, seed=21, device=cuda)
-    keep = ((rows // 3328) % 3 != 1) | (cols % 7 == 0)           # thin out every third doc block
+    keep = ((rows // bd) % 3 != 1) | (cols % 7 == 0)             # thin out every third doc block
     rows, cols, vals = rows[keep], cols[keep], vals[keep]
     index = ops.SparseDeviceIndex.from_coo(rows, cols, vals, n_terms, n_docs)
     lens = [0, 0, 0, 1, 150, 0, 1, 1, 0, 40, 0, 0, 97, 33, 32, 0, 64, 65, 0, 0, 2, 150, 0]
@@ -300,7 +301,7 @@ def test_ops_reject_cpu_tensors():
 def test_search_item_range_chunking(cuda, monkeypatch):
     """The kernel's item counter is 32 bits wide; launch_score cuts the doc-block range into launches of < 2^31 items.  The
     test hook lowers that limit so that every round is cut into many launches: results must not change."""
-    n_docs, n_terms, k = 3328 * 23 + 5, 2000, 100
+    n_docs, n_terms, k = ops.block_docs() * 23 + 5, 2000, 100
     rows, cols, vals = synth.gen_sparse_docs(n_docs, n_terms=n_terms, mean_nnz=20, seed=13, device=cuda)
     index = ops.SparseDeviceIndex.from_coo(rows, cols, vals, n_terms, n_docs)
     q_off, q_t, q_w = synth.gen_sparse_queries(50, n_terms=n_terms, mean_nnz=20, seed=14, device=cuda)
