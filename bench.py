@@ -49,11 +49,12 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-# torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; the CPU legs (reference arm, cpu_baseline) must use the
-# box's cores, so thread counts are set explicitly from host_cores() and never read from the environment.
+# torch.distributed.run exports OMP_NUM_THREADS=1 to every rank.  The CPU legs (reference arm, cpu_baseline) must use the box's
+# cores, so they pass thread counts EXPLICITLY (omp_set_num_threads through the oracle's n_threads argument,
+# torch.set_num_threads, numba.set_num_threads) and never read the environment; the GPU arm keeps the 1-thread default (with
+# N ranks x all-cores OpenMP teams spinning after every small host copy, the ranks' launch threads were starved: measured
+# -30 % end-to-end QPS at N = 2).
 HOST_CORES = host_cores()
-if os.environ.get("OMP_NUM_THREADS") == "1" and "LOCAL_RANK" in os.environ:
-    os.environ["OMP_NUM_THREADS"] = str(HOST_CORES)
 os.environ.setdefault("NUMBA_NUM_THREADS", str(HOST_CORES))
 
 import numpy as np  # noqa: E402
@@ -83,6 +84,22 @@ def load_peaks():
         return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p["bf16_tflops"]),
                 "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "source": "measured"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def ncu_traffic(kernel, launches_per_step, block_docs=None):
+    """DRAM bytes per launch of `kernel` from the committed ncu launch list of THIS kernel shape (profiles/r02_traffic.json, made
+    by tools/traffic_from_launches.py from profiles/r02_launches.csv), or None when the recorded shape / launch count per step
+    no longer matches what just ran (then the number would be stale).  bench.py itself cannot measure DRAM traffic."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        k = t["kernels"][kernel]
+        if abs(k["launches_per_step"] - launches_per_step) > 1e-9 or (block_docs is not None and t["sparse_block_docs"] != block_docs):
+            return None, None
+        return k["dram_bytes_per_launch"], f"profiles/r02_traffic.json <- {t['source']} ({k['launches']} launches under ncu)"
+    except (OSError, KeyError, ValueError):
+        return None, None
 
 
 class ClockSampler:
@@ -384,6 +401,7 @@ def bench_sparse(args, ctx):
         achieved = (algo_bytes * args.steps) / (score_ms / 1e3) / 1e9 if score_ms > 0 else 0.0
         peak = ctx.peaks["hbm_gbs"]
         build_gbs = nnz * 20 / (build_ms / 1e3) / 1e9
+        traffic, traffic_src = ncu_traffic("sparse_score_kernel", score_launches / args.steps, ops.block_docs()) if world == 1 else (None, None)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -403,14 +421,14 @@ def bench_sparse(args, ctx):
             "gpu_launches": int(all_launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "sparse_score_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": ctx.peaks["source"],
-                         "launches": int(score_launches), "avg_launch_ms": per_launch_ms,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": ctx.peaks["source"], "launches": int(score_launches), "avg_launch_ms": per_launch_ms,
                          "algorithmic_bytes_per_step": algo_bytes, "score_kernel_share_of_step": (score_ms / args.steps) / ms_per_step,
                          "select_kernels_ms_per_step": select_ms / args.steps,
                          "note": "algorithmic bytes = 8 B per (query, term) posting as the reference streams them; the kernel "
-                                 "re-serves postings shared between queries from L2 (DRAM traffic ~ the index once per step: "
-                                 "profiles/, ncu), so the limiter is the L1/shared data pipe, not DRAM; traffic is not "
-                                 "measured inside bench.py"},
+                                 "re-serves postings shared between queries from L2 (DRAM traffic ~ the index once per step), so "
+                                 "the limiter is the L1/shared data pipe (89 % under ncu), not DRAM; traffic = DRAM bytes per "
+                                 "launch from the committed ncu launch list of this kernel shape (null when it does not match)"},
             "build": {"kernel": "csr_build (radix sort)", "csr_build_ms": build_ms, "radix_sort_ms": sort_ms, "skip_table_s": table_s,
                       "synth_gen_s": gen_s, "postings": nnz, "algorithmic_bytes": nnz * 20, "achieved": build_gbs, "unit": "GB/s",
                       "peak": peak, "frac": build_gbs / peak},
@@ -552,6 +570,7 @@ def bench_dense(args, ctx, dim):
     if rank == 0:
         achieved = flops * args.steps / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
         peak = ctx.peaks["bf16_tflops"]
+        traffic, traffic_src = ncu_traffic("dense_search_kernel", gemm_launches / args.steps) if (world == 1 and dim == 2048) else (None, None)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -568,8 +587,8 @@ def bench_dense(args, ctx, dim):
             "gpu_launches": int(all_launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "dense_search_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": ctx.peaks["source"],
-                         "frac_of_sustained_peak": achieved / ctx.peaks["bf16_tflops_sustained"], "launches": int(gemm_launches),
+                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": ctx.peaks["source"], "frac_of_sustained_peak": achieved / ctx.peaks["bf16_tflops_sustained"], "launches": int(gemm_launches),
                          "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "algorithmic_flops_per_step": flops,
                          "gemm_kernel_share_of_step": (gemm_ms / args.steps) / ms_per_step,
                          "select_kernels_ms_per_step": select_ms / args.steps,
