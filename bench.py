@@ -326,7 +326,8 @@ def bench_sparse(args, ctx):
     del rows, cols, vals
     torch.cuda.empty_cache()
     t0 = time.perf_counter()
-    index = ops.SparseDeviceIndex.from_csr(term_offsets, doc_ids, weights, hi - lo)   # skip table + bank-ordered posting array
+    # skip table + bank-ordered posting array ({doc id, fp32 weight}; --sparse-weights fp16: the opt-in compressed 4-byte format)
+    index = ops.SparseDeviceIndex.from_csr(term_offsets, doc_ids, weights, hi - lo, weight_format=args.sparse_weights)
     torch.cuda.synchronize()
     table_s = time.perf_counter() - t0
     index.release_canonical()      # the search only streams index.postings; drop the 8 B/posting canonical copy
@@ -334,8 +335,12 @@ def bench_sparse(args, ctx):
     torch.cuda.empty_cache()
 
     q_off, q_terms, q_w = synth.gen_sparse_queries(n_queries, n_terms=n_terms, device=dev)
-    h_off, h_terms, h_w = q_off.cpu().numpy(), q_terms.cpu().numpy(), q_w.cpu().numpy()
-    algo_bytes, postings = synth.sparse_algorithmic_bytes(term_offsets, q_terms, n_queries, K_TOP)
+    # the step's inputs wait in PINNED host memory (the e2e contract): numpy views of pinned tensors
+    h_pins = [t.cpu().pin_memory() for t in (q_off, q_terms, q_w)]
+    h_off, h_terms, h_w = (t.numpy() for t in h_pins)
+    # (4 + w) bytes per streamed posting, w = 4 (fp32 weights, the parity and default mode) or 2 (fp16)
+    algo_bytes, postings = synth.sparse_algorithmic_bytes(term_offsets, q_terms, n_queries, K_TOP,
+                                                          weight_bytes=4 if args.sparse_weights == "fp32" else 2)
 
     def step():
         s, i, c = ops.sparse_search(index, q_off, q_terms, q_w, K_TOP, 0.0, doc_id_base=lo)
@@ -434,7 +439,9 @@ def bench_sparse(args, ctx):
                       "peak": peak, "frac": build_gbs / peak},
             "index_postings_this_rank": nnz, "postings_scored_per_query": postings / n_queries,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if args.sparse_weights != "fp32":
+            line["config"]["sparse_weights"] = args.sparse_weights + " (opt-in compressed postings; NOT the parity mode)"
+        if world == 1 and not args.no_cpu_baseline and args.sparse_weights == "fp32":
             # the oracle gets the same posting lists the GPU searched (slices in bank order; order inside a list is irrelevant)
             host = index.postings.cpu()
             h_ids, h_wts = host[:, 0].contiguous().numpy(), host[:, 1].contiguous().view(torch.float32).numpy()
@@ -522,7 +529,8 @@ def bench_dense(args, ctx, dim):
     corpus = synth.gen_dense(n_docs, dim, seed=1234, device=dev, dtype=torch.bfloat16, row_lo=lo, row_hi=hi)
     q32 = synth.gen_dense(n_queries, dim, seed=4321, device=dev)
     q16 = ops.f32_to_bf16(q32)
-    h_q = q32.cpu().numpy()
+    h_q_pin = q32.cpu().pin_memory()         # the step's input waits in PINNED host memory (the e2e contract)
+    h_q = h_q_pin.numpy()
     flops = 2.0 * n_queries * (hi - lo) * dim
 
     def step():
@@ -716,6 +724,8 @@ def main():
     ap.add_argument("--workload", default="both", choices=["both", "sparse", "dense"],
                     help="both (default) = sparse configs[1] at the top level + dense configs[2] (and configs[3] at N >= 8) as "
                          "sub-records; sparse / dense = that workload alone")
+    ap.add_argument("--sparse-weights", default="fp32", choices=["fp32", "fp16"],
+                    help="posting weights: fp32 = parity mode (default, the headline); fp16 = opt-in compressed 4-byte postings")
     ap.add_argument("--dim", type=int, default=2048, help="dense row width for --workload dense (2048 = Lion-DS-1B, 4096 = Lion-DS-8B)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -99,6 +99,16 @@ int b200ret_sparse_layout(const uint32_t* table, const int32_t* doc_ids, const f
                           int32_t n_terms, int32_t n_docs, int32_t block_docs, int bank_order,
                           void* postings_out, void* stream);
 
+/* Opt-in COMPRESSED posting format (north_star: "int32 doc ids, fp32 or fp16 weights"): postings_out[nnz] holds ONE 32-bit
+ * word per posting, fp16(weight, round-to-nearest-even) << 16 | (doc id - first doc id of its doc block), at the same CSR
+ * positions and in the same bank-quantile order as b200ret_sparse_layout.  4 B/posting instead of 8; searched with the
+ * *_f16 entry points below.  Scores are then the reference's arithmetic applied to the fp16-ROUNDED weights (bit-identical to
+ * numba_score_float run on weights.astype(float16).astype(float32)); they differ from the fp32-weight scores by up to
+ * 2^-11 relative per term, so this is not the parity format.  block_docs <= 32768. */
+int b200ret_sparse_layout_f16(const uint32_t* table, const int32_t* doc_ids, const float* weights, int64_t nnz,
+                              int32_t n_terms, int32_t n_docs, int32_t block_docs, int bank_order,
+                              void* postings_out, void* stream);
+
 /* Doc-block size (documents per warp-private accumulator tile) compiled into the search kernel. */
 int32_t b200ret_sparse_block_docs(void);
 
@@ -137,6 +147,19 @@ int b200ret_sparse_scores(const uint32_t* table, const void* postings,
                           const int32_t* q_offsets, const int32_t* q_terms, const float* q_weights,
                           int32_t n_queries, float* out_scores, void* workspace, size_t workspace_bytes,
                           void* stream);
+
+/* The same two calls over the compressed posting array of b200ret_sparse_layout_f16 (same arguments and outputs). */
+int b200ret_sparse_search_f16(const uint32_t* table, const void* postings,
+                              int32_t n_terms, int32_t n_docs, int32_t block_docs,
+                              const int32_t* q_offsets, const int32_t* q_terms, const float* q_weights,
+                              int32_t n_queries, int32_t k, float threshold, int64_t doc_id_base,
+                              float* out_scores, int64_t* out_ids, int32_t* out_counts,
+                              void* workspace, size_t workspace_bytes, void* stream);
+int b200ret_sparse_scores_f16(const uint32_t* table, const void* postings,
+                              int32_t n_terms, int32_t n_docs, int32_t block_docs,
+                              const int32_t* q_offsets, const int32_t* q_terms, const float* q_weights,
+                              int32_t n_queries, float* out_scores, void* workspace, size_t workspace_bytes,
+                              void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (3) Dense flat inner-product search.

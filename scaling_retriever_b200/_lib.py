@@ -29,6 +29,7 @@ PROTOTYPES = {
                                    _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_sz, _c_ptr]),
     "b200ret_block_table_build": (_c_int, [_c_ptr, _c_ptr, _c_i64, _c_i32, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_ptr]),
     "b200ret_sparse_layout": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i32, _c_i32, _c_i32, _c_int, _c_ptr, _c_ptr]),
+    "b200ret_sparse_layout_f16": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i32, _c_i32, _c_i32, _c_int, _c_ptr, _c_ptr]),
     "b200ret_sparse_block_docs": (_c_i32, []),
     "b200ret_sparse_search_workspace_bytes": (_c_sz, [_c_i32, _c_i32]),
     "b200ret_sparse_search": (_c_int, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32,
@@ -36,6 +37,11 @@ PROTOTYPES = {
                                        _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_sz, _c_ptr]),
     "b200ret_sparse_scores": (_c_int, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32,
                                        _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_ptr, _c_ptr, _c_sz, _c_ptr]),
+    "b200ret_sparse_search_f16": (_c_int, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32,
+                                           _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_f32, _c_i64,
+                                           _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_sz, _c_ptr]),
+    "b200ret_sparse_scores_f16": (_c_int, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32,
+                                           _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_ptr, _c_ptr, _c_sz, _c_ptr]),
     "b200ret_dense_search_workspace_bytes": (_c_sz, [_c_i32, _c_i32, _c_i32, _c_i32]),
     "b200ret_dense_search": (_c_int, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_i64,
                                       _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_sz, _c_ptr]),

@@ -1,7 +1,35 @@
 // Candidate-list kernels shared by the sparse and the dense search (declared in candidates.cuh).
 #include "candidates.cuh"
 
+#ifndef B200RET_SELECT_BULK      // 1 = a query's candidate list enters shared memory as ONE bulk asynchronous copy (TMA engine)
+#define B200RET_SELECT_BULK 1   //     instead of 8-byte loads by every thread (the select launches are bound by that load's latency)
+#endif
+
 namespace b200ret {
+
+namespace {
+__device__ __forceinline__ uint32_t sel_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+// global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned), completion counted on `bar`
+__device__ __forceinline__ void bulk_load_to_smem(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    const uint32_t b = sel_smem_u32(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sel_smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(b)
+                 : "memory");
+}
+__device__ __forceinline__ void bar_wait_phase0(uint64_t* bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}\n" ::"r"(sel_smem_u32(bar))
+        : "memory");
+}
+}  // namespace
 
 __global__ void cand_init_kernel(float* tau, int32_t* cand_count, int32_t* overflow, int32_t n_queries, float threshold) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -52,9 +80,24 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(uint64_t* cand, 
     if (!FINAL && c <= k) return;   // nothing to cut; tau keeps its value (block-uniform exit)
 
     const int n_sort = FINAL ? next_pow2(max(min(c, k), 1)) : 0;
+#if B200RET_SELECT_BULK
+    __shared__ __align__(8) uint64_t load_bar;
+    if (threadIdx.x == 0) {
+        out_pos = 0;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sel_smem_u32(&load_bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (c > 0) {     // block-uniform.  cap is even and the list starts 16-byte aligned, so an odd count copies one spare key
+        if (threadIdx.x == 0) bulk_load_to_smem(skeys, cq, static_cast<uint32_t>((c + 1) & ~1) * 8u, &load_bar);
+        bar_wait_phase0(&load_bar);
+    }
+    __syncthreads();
+#else
     for (int i = threadIdx.x; i < c; i += blockDim.x) skeys[i] = cq[i];
     if (threadIdx.x == 0) out_pos = 0;
     __syncthreads();
+#endif
     int kept = c;
     if (c > k) {
         const uint64_t kth = block_radix_select_kth(skeys, c, k, hist, bcast);

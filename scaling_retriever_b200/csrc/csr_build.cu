@@ -10,6 +10,8 @@
 // HBM-bound integer/byte work: every pass streams 12 B/posting in (coalesced, one posting per lane)
 // and 12 B/posting out; the grid is persistent (a multiple of the SM count) so the per-pass digit
 // table is tiny (buckets x blocks) and one CTA scans it.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace b200ret {
@@ -319,11 +321,26 @@ static inline size_t bank_warp_smem(int cap) { return static_cast<size_t>(cap) *
 
 // Output: the search-side posting array, (doc id, weight bits) interleaved as 8-byte elements at the SAME positions as the CSR
 // (so the skip table addresses both), every slice bank-ordered when `bank_order` is set, copied as is otherwise.
+// One posting of the search-side array.  FMT 0: {int32 doc id, fp32 weight} (8 bytes, the parity format).  FMT 1: one 32-bit
+// word, fp16(weight) << 16 | (doc id - first doc of the block) — the opt-in compressed format (round-to-nearest-even fp16
+// weights, 16-bit block-local doc ids): half the bytes per posting.
+template <int FMT>
+__device__ __forceinline__ void store_posting(void* out, size_t pos, int32_t doc, float w, int32_t block_first_doc) {
+    if (FMT == 0) {
+        static_cast<uint2*>(out)[pos] = make_uint2(static_cast<uint32_t>(doc), __float_as_uint(w));
+    } else {
+        const uint32_t h = __half_as_ushort(__float2half_rn(w));
+        static_cast<uint32_t*>(out)[pos] = (h << 16) | static_cast<uint32_t>(doc - block_first_doc);
+    }
+}
+
+template <int FMT>
 __global__ void __launch_bounds__(BANK_MAX_WARPS * 32) posting_layout_kernel(const uint32_t* __restrict__ table,
                                                                               const int32_t* __restrict__ doc_ids,
-                                                                              const float* __restrict__ weights, uint2* __restrict__ out,
+                                                                              const float* __restrict__ weights, void* __restrict__ out,
                                                                               int32_t n_terms, int32_t n_blocks, int32_t cap,
-                                                                              int32_t bank_order, int32_t min_len, int32_t max_len) {
+                                                                              int32_t bank_order, int32_t min_len, int32_t max_len,
+                                                                              int32_t block_docs) {
     extern __shared__ __align__(16) unsigned char bank_smem[];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
@@ -353,9 +370,9 @@ __global__ void __launch_bounds__(BANK_MAX_WARPS * 32) posting_layout_kernel(con
             todo &= todo - 1;
             const uint32_t s_beg = __shfl_sync(0xffffffffu, beg, j);
             const int len = static_cast<int>(__shfl_sync(0xffffffffu, end, j) - s_beg);
+            const int32_t first_doc = (static_cast<int>(item % groups) * 32 + j) * block_docs;     // of the slice's doc block
             if (len == 1 || !bank_order) {                     // nothing to reorder: interleave and copy
-                for (int i = lane; i < len; i += 32)
-                    out[s_beg + i] = make_uint2(static_cast<uint32_t>(doc_ids[s_beg + i]), __float_as_uint(weights[s_beg + i]));
+                for (int i = lane; i < len; i += 32) store_posting<FMT>(out, s_beg + i, doc_ids[s_beg + i], weights[s_beg + i], first_doc);
                 continue;
             }
             hist[lane] = 0;
@@ -392,7 +409,7 @@ __global__ void __launch_bounds__(BANK_MAX_WARPS * 32) posting_layout_kernel(con
             for (int i = lane; i < len; i += 32) {
                 const uint32_t ks = s_key[i];
                 const uint32_t pos = s_cnt[ks >> 8] + (ks & 0xffu);
-                out[s_beg + pos] = make_uint2(static_cast<uint32_t>(s_ids[i]), __float_as_uint(s_w[i]));
+                store_posting<FMT>(out, s_beg + pos, s_ids[i], s_w[i], first_doc);
             }
             __syncwarp();
         }
@@ -547,10 +564,9 @@ extern "C" int b200ret_block_table_build(const int64_t* term_offsets, const int3
     return B200RET_OK;
 }
 
-extern "C" int b200ret_sparse_layout(const uint32_t* table, const int32_t* doc_ids, const float* weights, int64_t nnz,
-                                     int32_t n_terms, int32_t n_docs, int32_t block_docs, int bank_order, void* postings_out,
-                                     void* stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+static int sparse_layout_impl(int fmt, const uint32_t* table, const int32_t* doc_ids, const float* weights, int64_t nnz,
+                              int32_t n_terms, int32_t n_docs, int32_t block_docs, int bank_order, void* postings_out,
+                              cudaStream_t stream) {
     B200RET_REQUIRE(table && n_terms > 0 && n_docs >= 0 && nnz >= 0, "sparse_layout: bad arguments");
     B200RET_REQUIRE(block_docs > 0 && block_docs <= BANK_MAX_BLOCK_DOCS && block_docs % 32 == 0,
                     "sparse_layout: block_docs=%d must be a multiple of 32 and <= %d", block_docs, BANK_MAX_BLOCK_DOCS);
@@ -560,7 +576,8 @@ extern "C" int b200ret_sparse_layout(const uint32_t* table, const int32_t* doc_i
     B200RET_REQUIRE(reinterpret_cast<uintptr_t>(postings_out) % 8 == 0, "sparse_layout: postings_out must be 8-byte aligned");
     static PerDeviceOnce attr_set;
     if (attr_set.first()) {
-        B200RET_CUDA_CHECK(cudaFuncSetAttribute(posting_layout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        B200RET_CUDA_CHECK(cudaFuncSetAttribute(posting_layout_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        B200RET_CUDA_CHECK(cudaFuncSetAttribute(posting_layout_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     }
     // Two launches: the shared memory of a warp is sized for the longest slice it may meet, and almost all slices are
     // short — sizing every warp for block_docs postings left 4 warps per SM and made the layout latency-bound (0.3 s).
@@ -570,10 +587,29 @@ extern "C" int b200ret_sparse_layout(const uint32_t* table, const int32_t* doc_i
         if (pass == 1 && caps[1] <= caps[0]) break;
         const int warps = max(1, min(BANK_MAX_WARPS, static_cast<int>((220 * 1024) / bank_warp_smem(caps[pass]))));
         const size_t smem = static_cast<size_t>(warps) * bank_warp_smem(caps[pass]);
-        posting_layout_kernel<<<sm_count(), warps * 32, smem, stream>>>(table, doc_ids, weights, static_cast<uint2*>(postings_out),
-                                                                       n_terms, n_blocks, caps[pass], bank_order, mins[pass], caps[pass]);
+        if (fmt == 0)
+            posting_layout_kernel<0><<<sm_count(), warps * 32, smem, stream>>>(table, doc_ids, weights, postings_out, n_terms, n_blocks,
+                                                                              caps[pass], bank_order, mins[pass], caps[pass], block_docs);
+        else
+            posting_layout_kernel<1><<<sm_count(), warps * 32, smem, stream>>>(table, doc_ids, weights, postings_out, n_terms, n_blocks,
+                                                                              caps[pass], bank_order, mins[pass], caps[pass], block_docs);
         count_launches(1);
     }
     B200RET_CUDA_CHECK(cudaGetLastError());
     return B200RET_OK;
+}
+
+extern "C" int b200ret_sparse_layout(const uint32_t* table, const int32_t* doc_ids, const float* weights, int64_t nnz,
+                                     int32_t n_terms, int32_t n_docs, int32_t block_docs, int bank_order, void* postings_out,
+                                     void* stream_) {
+    return sparse_layout_impl(0, table, doc_ids, weights, nnz, n_terms, n_docs, block_docs, bank_order, postings_out,
+                              static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int b200ret_sparse_layout_f16(const uint32_t* table, const int32_t* doc_ids, const float* weights, int64_t nnz,
+                                         int32_t n_terms, int32_t n_docs, int32_t block_docs, int bank_order, void* postings_out,
+                                         void* stream_) {
+    B200RET_REQUIRE(block_docs <= 32768, "sparse_layout_f16: block-local doc ids take 15 bits (block_docs=%d)", block_docs);
+    return sparse_layout_impl(1, table, doc_ids, weights, nnz, n_terms, n_docs, block_docs, bank_order, postings_out,
+                              static_cast<cudaStream_t>(stream_));
 }

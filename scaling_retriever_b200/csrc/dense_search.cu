@@ -346,7 +346,7 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int32_t di
     return B200RET_OK;
 }
 
-static int dense_cap(int k) { return k + max(D_ROUND0_DOCS, (ROUND_GROWTH + 1) * k); }   // see search_cap (sparse_search.cu)
+static int dense_cap(int k) { return (k + max(D_ROUND0_DOCS, (ROUND_GROWTH + 1) * k) + 1) & ~1; }   // see search_cap (sparse_search.cu)
 
 }  // namespace b200ret
 

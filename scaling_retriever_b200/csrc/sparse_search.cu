@@ -109,7 +109,9 @@ static_assert(SCORE_SMEM <= 227 * 1024, "exceeds the shared memory of one SM");
 struct ScoreParams {
     const uint32_t* table;     // [n_terms][table_stride]
     size_t table_stride;       // n_blocks + 1
-    const uint2* postings;     // [nnz] {doc id, weight bits}, CSR positions (b200ret_sparse_layout)
+    const void* postings;      // [nnz] postings at the CSR positions: {doc id, fp32 weight} (b200ret_sparse_layout) or the packed
+                               // 32-bit fp16 format (b200ret_sparse_layout_f16)
+    int32_t format;            // 0 / 1 (host side only: selects the kernel instantiation)
     const int32_t* q_offsets;
     const int32_t* q_terms;
     const float* q_weights;
@@ -353,7 +355,12 @@ __device__ __forceinline__ unsigned prime_pipeline(const ScoreParams& p, uint32_
     return nn;
 }
 
+// FMT 0: 8-byte postings {int32 doc id, fp32 weight} — the parity format (bit-identical to numba_score_float).
+// FMT 1: 4-byte postings fp16(weight) << 16 | block-local doc id — the opt-in compressed format: same arithmetic on the
+//        fp16-rounded weights (bit-identical to the oracle run on those), half the global-load wavefronts per row.
+template <int FMT>
 __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __grid_constant__ ScoreParams p) {
+    constexpr int PBYTES = FMT ? 4 : 8;
     constexpr int BD = BLOCK_DOCS, R = STEP_ROWS;
     extern __shared__ __align__(16) float smem_acc[];
     const unsigned lane = lane_id();
@@ -366,7 +373,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
     const uint32_t desc_s01 = 2u * static_cast<uint32_t>(__cvta_generic_to_shared(ctrl + CTRL_DESC)) + DESC_BUF_WORDS * 4u;
     uint32_t desc_s = static_cast<uint32_t>(__cvta_generic_to_shared(ctrl + CTRL_DESC)) + DESC_BUF_WORDS * 4u;
     const uint32_t acc_s = static_cast<uint32_t>(__cvta_generic_to_shared(acc));
-    const uint2* __restrict__ const g_post = p.postings + lane;     // lane-private base: address = base + row position
+    const char* __restrict__ const g_post = static_cast<const char*>(p.postings) + lane * PBYTES;     // lane-private base
 
     for (int i = lane * 4; i < BD; i += 128) *reinterpret_cast<float4*>(acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
@@ -383,7 +390,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
     // branches around the rows past a short slice were measured slower than the dead L1 data-pipe slots they save.
     // advance(): branch-free cursor step; every state change is predicated on "slice exhausted and another one pending".
     // len == 0 on return: the group is exhausted (refill below).
-    auto advance = [&](float& qw, unsigned& rel, unsigned& len, const uint2*& row0) {
+    auto advance = [&](float& qw, unsigned& rel, unsigned& len, const char*& row0) {
         asm volatile(
             "{\n\t"
             ".reg .pred adv, have, take, dead;\n\t"
@@ -445,10 +452,10 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
 #if B200RET_ADDR32
         const unsigned pos = c_row + lane;          // < nnz < 2^32 (csr_build rejects larger indexes): 32-bit sum, one widening multiply-add
         rel = pos - c_beg;
-        row0 = p.postings + pos;
+        row0 = static_cast<const char*>(p.postings) + static_cast<size_t>(pos) * PBYTES;
 #else
         rel = c_row + lane - c_beg;
-        row0 = g_post + c_row;     // one 64-bit address per step; rows are 256 bytes apart (immediates)
+        row0 = g_post + static_cast<size_t>(c_row) * PBYTES;     // one 64-bit address per step; rows are 32 postings apart (immediates)
 #endif
         c_row += 32u * R;
     };
@@ -458,38 +465,58 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
     // it (dep >> 31 == 0 is added to the lane position), so they cannot be issued before that batch's loads have landed —
     // see the main loop for why this order matters.
     auto fetch = [&](int (&id)[R], float (&w)[R], float& qw, unsigned& rel, unsigned& len, int dep) {
-        const uint2* row0;
+        const char* row0;
         advance(qw, rel, len, row0);
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p0, p1, p2, p3;\n\t"
-            ".reg .u32 t0, t1, t2, t3;\n\t"
-            "shr.u32 t0, %11, 31;\n\t"
-            "add.u32 t0, t0, %8;\n\t"
 #if B200RET_PRED_MODE == 0
-            "add.u32 t1, t0, 32;\n\t"
-            "add.u32 t2, t0, 64;\n\t"
-            "add.u32 t3, t0, 96;\n\t"
-            "setp.lt.u32 p0, t0, %9;\n\t"
-            "setp.lt.u32 p1, t1, %9;\n\t"
-            "setp.lt.u32 p2, t2, %9;\n\t"
+#define B200RET_FETCH_PRED                  \
+            "add.u32 t1, t0, 32;\n\t"       \
+            "add.u32 t2, t0, 64;\n\t"       \
+            "add.u32 t3, t0, 96;\n\t"       \
+            "setp.lt.u32 p0, t0, %9;\n\t"   \
+            "setp.lt.u32 p1, t1, %9;\n\t"   \
+            "setp.lt.u32 p2, t2, %9;\n\t"   \
             "setp.lt.u32 p3, t3, %9;\n\t"
 #else       // u = len - rel as a SIGNED count of postings from this lane's row-0 position to the slice end: row r >= 1 is live iff
             // u > 32 r (lanes before the slice begin have rel = -x, u = len + x; lanes past the end have u <= 0); row 0 also
             // needs rel >= 0, i.e. the unsigned rel < len
-            "sub.s32 t1, %9, t0;\n\t"
-            "setp.lt.u32 p0, t0, %9;\n\t"
-            "setp.gt.s32 p1, t1, 32;\n\t"
-            "setp.gt.s32 p2, t1, 64;\n\t"
+#define B200RET_FETCH_PRED                  \
+            "sub.s32 t1, %9, t0;\n\t"       \
+            "setp.lt.u32 p0, t0, %9;\n\t"   \
+            "setp.gt.s32 p1, t1, 32;\n\t"   \
+            "setp.gt.s32 p2, t1, 64;\n\t"   \
             "setp.gt.s32 p3, t1, 96;\n\t"
 #endif
-            "@p0 " B200RET_LDNC ".v2.b32 {%0, %4}, [%10];\n\t"          // one posting = {doc id, weight bits}
-            "@p1 " B200RET_LDNC ".v2.b32 {%1, %5}, [%10 + 256];\n\t"
-            "@p2 " B200RET_LDNC ".v2.b32 {%2, %6}, [%10 + 512];\n\t"
-            "@p3 " B200RET_LDNC ".v2.b32 {%3, %7}, [%10 + 768];\n\t"
-            "}\n"
-            : "+r"(id[0]), "+r"(id[1]), "+r"(id[2]), "+r"(id[3]), "+f"(w[0]), "+f"(w[1]), "+f"(w[2]), "+f"(w[3])
-            : "r"(rel), "r"(len), "l"(row0), "r"(dep));
+        if (FMT == 0) {
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p0, p1, p2, p3;\n\t"
+                ".reg .u32 t0, t1, t2, t3;\n\t"
+                "shr.u32 t0, %11, 31;\n\t"
+                "add.u32 t0, t0, %8;\n\t"
+                B200RET_FETCH_PRED
+                "@p0 " B200RET_LDNC ".v2.b32 {%0, %4}, [%10];\n\t"          // one posting = {doc id, weight bits}
+                "@p1 " B200RET_LDNC ".v2.b32 {%1, %5}, [%10 + 256];\n\t"
+                "@p2 " B200RET_LDNC ".v2.b32 {%2, %6}, [%10 + 512];\n\t"
+                "@p3 " B200RET_LDNC ".v2.b32 {%3, %7}, [%10 + 768];\n\t"
+                "}\n"
+                : "+r"(id[0]), "+r"(id[1]), "+r"(id[2]), "+r"(id[3]), "+f"(w[0]), "+f"(w[1]), "+f"(w[2]), "+f"(w[3])
+                : "r"(rel), "r"(len), "l"(row0), "r"(dep));
+        } else {     // packed postings: one 32-bit word each; bit 15 of a word (block-local doc ids are < 2^15) is the always-0 dependency
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p0, p1, p2, p3;\n\t"
+                ".reg .u32 t0, t1, t2, t3;\n\t"
+                "bfe.u32 t0, %11, 15, 1;\n\t"
+                "add.u32 t0, t0, %8;\n\t"
+                B200RET_FETCH_PRED
+                "@p0 " B200RET_LDNC ".b32 %0, [%10];\n\t"
+                "@p1 " B200RET_LDNC ".b32 %1, [%10 + 128];\n\t"
+                "@p2 " B200RET_LDNC ".b32 %2, [%10 + 256];\n\t"
+                "@p3 " B200RET_LDNC ".b32 %3, [%10 + 384];\n\t"
+                "}\n"
+                : "+r"(id[0]), "+r"(id[1]), "+r"(id[2]), "+r"(id[3]), "+f"(w[0]), "+f"(w[1]), "+f"(w[2]), "+f"(w[3])
+                : "r"(rel), "r"(len), "l"(row0), "r"(dep));
+        }
     };
     // Accumulate one step.  Its rows belong to ONE posting list, so their doc ids are distinct and the R
     // read-modify-writes are independent: loads, adds and stores are issued R-wide (one latency per step).
@@ -497,14 +524,40 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
     // acc_rel_s: shared-memory byte address such that acc_rel_s + 4 * doc_id is the doc's score slot.
     // In two parts: the score-slot addresses (first use of the loaded doc ids: the scoreboard wait for the batch's loads
     // happens here), and the read-modify-writes.
-    auto consume_pre = [&](const int (&id)[R], uint32_t (&d)[R], uint32_t acc_rel_s) {
-        asm volatile(
-            "mad.lo.u32 %0, %4, 4, %8;\n\t"
-            "mad.lo.u32 %1, %5, 4, %8;\n\t"
-            "mad.lo.u32 %2, %6, 4, %8;\n\t"
-            "mad.lo.u32 %3, %7, 4, %8;\n"
-            : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
-            : "r"(id[0]), "r"(id[1]), "r"(id[2]), "r"(id[3]), "r"(acc_rel_s));
+    auto consume_pre = [&](const int (&id)[R], float (&w)[R], uint32_t (&d)[R], uint32_t acc_rel_s) {
+        if (FMT == 0) {
+            asm volatile(
+                "mad.lo.u32 %0, %4, 4, %8;\n\t"
+                "mad.lo.u32 %1, %5, 4, %8;\n\t"
+                "mad.lo.u32 %2, %6, 4, %8;\n\t"
+                "mad.lo.u32 %3, %7, 4, %8;\n"
+                : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+                : "r"(id[0]), "r"(id[1]), "r"(id[2]), "r"(id[3]), "r"(acc_rel_s));
+        } else {     // word = fp16 weight << 16 | block-local doc id: slot address from the low half, fp32 weight from the high half
+            asm volatile(
+                "{\n\t"
+                ".reg .b16 l0, l1, l2, l3, h0, h1, h2, h3;\n\t"
+                ".reg .u32 u0, u1, u2, u3;\n\t"
+                "mov.b32 {l0, h0}, %8;\n\t"
+                "mov.b32 {l1, h1}, %9;\n\t"
+                "mov.b32 {l2, h2}, %10;\n\t"
+                "mov.b32 {l3, h3}, %11;\n\t"
+                "cvt.u32.u16 u0, l0;\n\t"
+                "cvt.u32.u16 u1, l1;\n\t"
+                "cvt.u32.u16 u2, l2;\n\t"
+                "cvt.u32.u16 u3, l3;\n\t"
+                "mad.lo.u32 %0, u0, 4, %12;\n\t"
+                "mad.lo.u32 %1, u1, 4, %12;\n\t"
+                "mad.lo.u32 %2, u2, 4, %12;\n\t"
+                "mad.lo.u32 %3, u3, 4, %12;\n\t"
+                "cvt.f32.f16 %4, h0;\n\t"
+                "cvt.f32.f16 %5, h1;\n\t"
+                "cvt.f32.f16 %6, h2;\n\t"
+                "cvt.f32.f16 %7, h3;\n\t"
+                "}\n"
+                : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=f"(w[0]), "=f"(w[1]), "=f"(w[2]), "=f"(w[3])
+                : "r"(id[0]), "r"(id[1]), "r"(id[2]), "r"(id[3]), "r"(acc_rel_s));
+        }
     };
     auto consume_rest = [&](const uint32_t (&d)[R], const float (&w)[R], float qw, unsigned rel, unsigned len) {
         asm volatile(
@@ -571,7 +624,8 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
         }
     }
     FetchStages fs(p, ctrl, lane);
-    uint32_t acc_rel_s = acc_s - static_cast<uint32_t>(st.a_blk * BD) * 4u;   // tile base of the first item (group a)
+    // tile base of the first item (group a); packed postings carry block-local doc ids, so their base never moves
+    uint32_t acc_rel_s = FMT ? acc_s : acc_s - static_cast<uint32_t>(st.a_blk * BD) * 4u;
     bool sweep_due = false, fin = false;
     int sw_q = 0, sw_doc_base = 0;
     float sw_tau = 0.f;
@@ -579,7 +633,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
     auto half = [&](int c0, int f0) {     // accumulate batch [c0, c0 + HB) while the loads of batch [f0, f0 + HB) are issued
         uint32_t d[HB][R];
 #pragma unroll
-        for (int s = 0; s < HB; ++s) consume_pre(id[c0 + s], d[s], acc_rel_s);
+        for (int s = 0; s < HB; ++s) consume_pre(id[c0 + s], w[c0 + s], d[s], acc_rel_s);
 #pragma unroll
         for (int s = 0; s < HB; ++s) fetch(id[f0 + s], w[f0 + s], qw[f0 + s], rel[f0 + s], len[f0 + s], id[c0][0]);
 #pragma unroll
@@ -595,7 +649,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) sparse_score_kernel(const __
                 sw_q = st.k_q;
                 sw_doc_base = st.k_blk * BD;
                 sw_tau = p.tau ? __ldg(p.tau + sw_q) : 0.f;   // arrives while A is accumulated
-                sw_next_acc_rel = acc_s - static_cast<uint32_t>(((flags & A_VALID) ? st.a_blk : st.k_blk) * BD) * 4u;
+                sw_next_acc_rel = FMT ? acc_s : acc_s - static_cast<uint32_t>(((flags & A_VALID) ? st.a_blk : st.k_blk) * BD) * 4u;
                 flags |= K_MARKED;
                 __syncwarp();                                 // stash: reads above, write below
                 fs.st.flags = flags;
@@ -640,7 +694,9 @@ static int block_docs_of_shape() { return BLOCK_DOCS; }
 static int launch_score(const ScoreParams& sp, cudaStream_t stream) {
     static PerDeviceOnce attr_set;
     if (attr_set.first()) {
-        B200RET_CUDA_CHECK(cudaFuncSetAttribute(sparse_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        B200RET_CUDA_CHECK(cudaFuncSetAttribute(sparse_score_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                static_cast<int>(SCORE_SMEM)));
+        B200RET_CUDA_CHECK(cudaFuncSetAttribute(sparse_score_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 static_cast<int>(SCORE_SMEM)));
     }
     // The item counter is 32 bits wide (claims run past the end by a few per warp): cut the block range so that one
@@ -655,7 +711,10 @@ static int launch_score(const ScoreParams& sp, cudaStream_t stream) {
         r.blk_end = std::min(sp.blk_end, b0 + max_blocks);
         B200RET_CUDA_CHECK(cudaMemsetAsync(r.item_counter, 0, sizeof(unsigned), stream));
         prof_begin(PROF_SPARSE_SCORE, stream);
-        sparse_score_kernel<<<sm_count(), SCORE_THREADS, SCORE_SMEM, stream>>>(r);
+        if (r.format == 0)
+            sparse_score_kernel<0><<<sm_count(), SCORE_THREADS, SCORE_SMEM, stream>>>(r);
+        else
+            sparse_score_kernel<1><<<sm_count(), SCORE_THREADS, SCORE_SMEM, stream>>>(r);
         prof_end(PROF_SPARSE_SCORE, stream);
         count_launches(1);
         B200RET_CUDA_CHECK(cudaGetLastError());
@@ -665,7 +724,7 @@ static int launch_score(const ScoreParams& sp, cudaStream_t stream) {
 
 // candidate capacity: the k kept keys + what one round may append — the first round's docs, or for large k the ~(ROUND_GROWTH - 1) * k
 // survivors a geometric round is expected to produce, with a two-k margin (candidates.cuh)
-static int search_cap(int k) { return k + std::max(ROUND0_BLOCKS * block_docs_of_shape(), (ROUND_GROWTH + 1) * k); }
+static int search_cap(int k) { return (k + std::max(ROUND0_BLOCKS * block_docs_of_shape(), (ROUND_GROWTH + 1) * k) + 1) & ~1; }   // even: lists stay 16-byte aligned
 
 }  // namespace b200ret
 
@@ -687,7 +746,7 @@ static int fill_params(ScoreParams& sp, const uint32_t* table, const void* posti
     sp = ScoreParams{};
     sp.table = table;
     sp.table_stride = static_cast<size_t>(n_blocks) + 1;
-    sp.postings = static_cast<const uint2*>(postings);
+    sp.postings = postings;
     sp.q_offsets = q_offsets;
     sp.q_terms = q_terms;
     sp.q_weights = q_weights;
@@ -696,16 +755,17 @@ static int fill_params(ScoreParams& sp, const uint32_t* table, const void* posti
     return B200RET_OK;
 }
 
-extern "C" int b200ret_sparse_scores(const uint32_t* table, const void* postings,
-                                     int32_t n_terms, int32_t n_docs, int32_t block_docs,
-                                     const int32_t* q_offsets, const int32_t* q_terms, const float* q_weights,
-                                     int32_t n_queries, float* out_scores, void* workspace, size_t workspace_bytes,
-                                     void* stream_) {
+static int sparse_scores_impl(int format, const uint32_t* table, const void* postings,
+                              int32_t n_terms, int32_t n_docs, int32_t block_docs,
+                              const int32_t* q_offsets, const int32_t* q_terms, const float* q_weights,
+                              int32_t n_queries, float* out_scores, void* workspace, size_t workspace_bytes,
+                              void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     B200RET_REQUIRE(n_queries >= 0 && n_docs >= 0 && n_terms > 0, "sparse_scores: bad sizes");
     ScoreParams sp;
     int rc = fill_params(sp, table, postings, n_docs, block_docs, q_offsets, q_terms, q_weights, n_queries);
     if (rc != B200RET_OK) return rc;
+    sp.format = format;
     if (n_queries == 0 || n_docs == 0) return B200RET_OK;
     B200RET_REQUIRE(table && q_offsets && out_scores && workspace && workspace_bytes >= 256, "sparse_scores: null pointer / workspace < 256 B");
     const int32_t n_blocks = static_cast<int32_t>(sp.table_stride) - 1;
@@ -717,16 +777,31 @@ extern "C" int b200ret_sparse_scores(const uint32_t* table, const void* postings
     return launch_score(sp, stream);
 }
 
-extern "C" int b200ret_sparse_search(const uint32_t* table, const void* postings,
-                                     int32_t n_terms, int32_t n_docs, int32_t block_docs,
-                                     const int32_t* q_offsets, const int32_t* q_terms, const float* q_weights,
-                                     int32_t n_queries, int32_t k, float threshold, int64_t doc_id_base,
-                                     float* out_scores, int64_t* out_ids, int32_t* out_counts,
-                                     void* workspace, size_t workspace_bytes, void* stream_) {
+extern "C" int b200ret_sparse_scores(const uint32_t* table, const void* postings, int32_t n_terms, int32_t n_docs, int32_t block_docs,
+                                     const int32_t* q_offsets, const int32_t* q_terms, const float* q_weights, int32_t n_queries,
+                                     float* out_scores, void* workspace, size_t workspace_bytes, void* stream) {
+    return sparse_scores_impl(0, table, postings, n_terms, n_docs, block_docs, q_offsets, q_terms, q_weights, n_queries, out_scores,
+                              workspace, workspace_bytes, stream);
+}
+
+extern "C" int b200ret_sparse_scores_f16(const uint32_t* table, const void* postings, int32_t n_terms, int32_t n_docs,
+                                         int32_t block_docs, const int32_t* q_offsets, const int32_t* q_terms, const float* q_weights,
+                                         int32_t n_queries, float* out_scores, void* workspace, size_t workspace_bytes, void* stream) {
+    return sparse_scores_impl(1, table, postings, n_terms, n_docs, block_docs, q_offsets, q_terms, q_weights, n_queries, out_scores,
+                              workspace, workspace_bytes, stream);
+}
+
+static int sparse_search_impl(int format, const uint32_t* table, const void* postings,
+                              int32_t n_terms, int32_t n_docs, int32_t block_docs,
+                              const int32_t* q_offsets, const int32_t* q_terms, const float* q_weights,
+                              int32_t n_queries, int32_t k, float threshold, int64_t doc_id_base,
+                              float* out_scores, int64_t* out_ids, int32_t* out_counts,
+                              void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     ScoreParams sp;
     int rc = fill_params(sp, table, postings, n_docs, block_docs, q_offsets, q_terms, q_weights, n_queries);
     if (rc != B200RET_OK) return rc;
+    sp.format = format;
     B200RET_REQUIRE(k >= 1 && k <= B200RET_MAX_K, "sparse_search: k=%d outside [1, %d]", k, B200RET_MAX_K);
     B200RET_REQUIRE(n_queries >= 0 && n_docs >= 0 && n_terms > 0, "sparse_search: bad sizes");
     if (n_queries == 0) return B200RET_OK;
@@ -756,4 +831,20 @@ extern "C" int b200ret_sparse_search(const uint32_t* table, const void* postings
     };
     return run_search(launch_round, b, cap, k, n_queries, n_blocks, ROUND0_BLOCKS, threshold, doc_id_base, out_scores, out_ids,
                       out_counts, stream);
+}
+
+extern "C" int b200ret_sparse_search(const uint32_t* table, const void* postings, int32_t n_terms, int32_t n_docs, int32_t block_docs,
+                                     const int32_t* q_offsets, const int32_t* q_terms, const float* q_weights, int32_t n_queries,
+                                     int32_t k, float threshold, int64_t doc_id_base, float* out_scores, int64_t* out_ids,
+                                     int32_t* out_counts, void* workspace, size_t workspace_bytes, void* stream) {
+    return sparse_search_impl(0, table, postings, n_terms, n_docs, block_docs, q_offsets, q_terms, q_weights, n_queries, k, threshold,
+                              doc_id_base, out_scores, out_ids, out_counts, workspace, workspace_bytes, stream);
+}
+
+extern "C" int b200ret_sparse_search_f16(const uint32_t* table, const void* postings, int32_t n_terms, int32_t n_docs,
+                                         int32_t block_docs, const int32_t* q_offsets, const int32_t* q_terms, const float* q_weights,
+                                         int32_t n_queries, int32_t k, float threshold, int64_t doc_id_base, float* out_scores,
+                                         int64_t* out_ids, int32_t* out_counts, void* workspace, size_t workspace_bytes, void* stream) {
+    return sparse_search_impl(1, table, postings, n_terms, n_docs, block_docs, q_offsets, q_terms, q_weights, n_queries, k, threshold,
+                              doc_id_base, out_scores, out_ids, out_counts, workspace, workspace_bytes, stream);
 }

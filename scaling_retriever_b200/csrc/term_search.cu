@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(T_THREADS) term_gather_kernel(const TermParams
     }
 }
 
-static int term_cap(int k) { return k + max(T_ROUND0_UNITS * T_UNIT_DOCS, (ROUND_GROWTH + 1) * k); }
+static int term_cap(int k) { return (k + max(T_ROUND0_UNITS * T_UNIT_DOCS, (ROUND_GROWTH + 1) * k) + 1) & ~1; }
 
 static int launch_term(TermParams r, int32_t n_vocab, cudaStream_t stream) {
     const bool in_smem = n_vocab <= T_MAX_SMEM_VOCAB;

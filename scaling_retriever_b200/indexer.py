@@ -67,7 +67,12 @@ def _pinned(staging, name, shape, dtype):
 
 
 def _stage_in(staging, device, name, host_array, dtype):
-    src = torch.from_numpy(np.ascontiguousarray(host_array)).to(dtype)
+    """Host array -> device tensor.  Pageable input goes through a reusable pinned staging buffer; an input that already lives
+    in pinned memory (a numpy view of a pinned tensor) is copied straight from where it is."""
+    src = torch.from_numpy(np.ascontiguousarray(host_array))
+    if src.dtype == dtype and src.numel() and src.is_pinned():
+        return src.to(device, non_blocking=True)
+    src = src.to(dtype)
     pinned = _pinned(staging, name, tuple(src.shape), dtype)
     pinned.copy_(src)
     return pinned.to(device, non_blocking=True)
@@ -355,7 +360,8 @@ class DenseFlatIndexer(DenseIndexer):
         logger.info("total data indexed %d", n_total)
 
     def search_arrays(self, query_reps, top_docs, host_ranks="all"):
-        """(scores fp32 [Q, k] descending, row labels int64 [Q, k], -1 padded) as host numpy arrays.
+        """(scores fp32 [Q, k] descending, row labels int64 [Q, k], -1 padded) as host numpy arrays — VIEWS of reusable pinned
+        buffers, overwritten by the next call of this object (search_knn returns copies).
         `host_ranks="first"` (sharded search only): the merged result is copied to the host of the first worker alone — the
         rank that writes the run file — and the other ranks return (None, None)."""
         if self.index is None or self.device is None:
@@ -562,7 +568,9 @@ class SparseRetrieval:
             self.shard_plan = shard.ShardPlan(self.size_collection, _world_size())
             lo, hi = self.shard_plan.bounds(_rank()) if self.shard_plan.world_size > 1 else (0, self.size_collection)
             # one search-side index normally; several consecutive doc ranges when this rank's share holds >= 2^32 postings
-            self.device_shards = self.sparse_index.device_shards(lo, hi, kwargs.get("max_shard_postings") or MAX_SHARD_POSTINGS)
+            # kwargs (swallowed like the reference's **kwargs): weight_format="fp16" selects the compressed posting array
+            self.device_shards = self.sparse_index.device_shards(lo, hi, kwargs.get("max_shard_postings") or MAX_SHARD_POSTINGS,
+                                                                 kwargs.get("weight_format", "fp32"))
             self.device_index, self.doc_id_base = self.device_shards[0]
 
         self.out_dir = os.path.join(config["out_dir"], dataset_name) if (dataset_name is not None and not is_beir) \
@@ -598,7 +606,8 @@ class SparseRetrieval:
     # ---- the hot path -----------------------------------------------------------------------------------------
     def search_arrays(self, q_offsets, q_terms, q_weights, topk, threshold=0.0, host_ranks="all"):
         """HOST query arrays -> HOST result arrays (scores fp32 [Q,k], row ids int64 [Q,k], counts int32 [Q]).
-        Copies through pinned memory; this is the call bench.py times end to end.  `host_ranks="first"` (sharded search
+        Copies through pinned memory; this is the call bench.py times end to end.  The returned arrays are VIEWS of reusable
+        pinned buffers: the next search_arrays call of this object overwrites them (copy what must be kept).  `host_ranks="first"` (sharded search
         only): the merged result goes to the host of the first worker alone — the rank that writes run.json — and the
         other ranks return (None, None, None)."""
         dev = self._cuda

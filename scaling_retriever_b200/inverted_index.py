@@ -239,7 +239,7 @@ class IndexDictOfArray:
         json.dump(index_dist, open(os.path.join(self.index_path, "index_dist.json"), "w"))
 
     # ---- search-side view -----------------------------------------------------------------------------------
-    def device_shards(self, doc_lo=0, doc_hi=None, max_postings=MAX_SHARD_POSTINGS):
+    def device_shards(self, doc_lo=0, doc_hi=None, max_postings=MAX_SHARD_POSTINGS, weight_format="fp32"):
         """[(SparseDeviceIndex, first doc row)] covering doc rows [doc_lo, doc_hi): ONE entry normally; a range that holds more
         postings than the kernels' 32-bit positions address (>= 2^32, e.g. 20 M docs x 200 terms on one GPU) is cut into
         consecutive doc ranges that are searched one after the other and merged (SparseRetrieval.search_arrays)."""
@@ -247,14 +247,14 @@ class IndexDictOfArray:
         nnz = len(self._csr_host[1]) if self._csr_host is not None else (self._csr_dev[1].numel() if self._csr_dev is not None else
                                                                           sum(r.numel() for r, _, _ in self._log))
         if nnz <= max_postings:
-            return [(self.device_index(doc_lo, doc_hi), doc_lo)]
+            return [(self.device_index(doc_lo, doc_hi, weight_format), doc_lo)]
         if self._csr_host is None:
             raise NotImplementedError(f"an index of {nnz} postings built in memory exceeds the 32-bit posting positions of one "
                                       "CSR build; save and load it (the loader cuts it into doc ranges), or index under torchrun")
         off, ids, _ = self._csr_host
-        return [(self.device_index(a, b), a) for a, b in split_doc_range(off, ids, doc_lo, doc_hi, max_postings)]
+        return [(self.device_index(a, b, weight_format), a) for a, b in split_doc_range(off, ids, doc_lo, doc_hi, max_postings)]
 
-    def device_index(self, doc_lo=0, doc_hi=None):
+    def device_index(self, doc_lo=0, doc_hi=None, weight_format="fp32"):
         """Search-side index on the GPU for doc rows [doc_lo, doc_hi) (default: all; row ids become local to the range):
         doc-sorted CSR + doc-block skip table, slices in bank order.  The canonical CSR of this object is not modified."""
         n_docs = int(self.n)
@@ -274,7 +274,7 @@ class IndexDictOfArray:
                 off, ids, w = shard.shard_sparse_csr(off, ids, w, doc_lo, doc_hi)
                 n_docs = doc_hi - doc_lo
         try:
-            return ops.SparseDeviceIndex.from_csr(off, ids, w, n_docs)
+            return ops.SparseDeviceIndex.from_csr(off, ids, w, n_docs, weight_format=weight_format)
         except Exception as exc:   # lists not ascending (merged multi-rank index): re-sort by (term, doc) on the GPU
             from ._lib import B200RetError
             if not (isinstance(exc, B200RetError) and exc.code == -4):
@@ -282,7 +282,7 @@ class IndexDictOfArray:
         counts = (off[1:] - off[:-1])
         cols = torch.repeat_interleave(torch.arange(off.numel() - 1, dtype=torch.int32, device=off.device), counts,
                                        output_size=ids.numel())
-        return ops.SparseDeviceIndex.from_coo(ids, cols, w, off.numel() - 1, n_docs)
+        return ops.SparseDeviceIndex.from_coo(ids, cols, w, off.numel() - 1, n_docs, weight_format=weight_format)
 
 
 def split_doc_range(off, ids, lo, hi, max_postings):

@@ -109,10 +109,12 @@ class SparseDeviceIndex:
     doc_ids: torch.Tensor        # int32 [nnz], ascending inside each term (None after release_canonical)
     weights: torch.Tensor        # fp32 [nnz] (None after release_canonical)
     table: torch.Tensor          # int32 storage of uint32 [n_terms, n_blocks + 1]
-    postings: torch.Tensor       # int32 [nnz, 2]: column 0 doc id, column 1 fp32 weight bits
+    postings: torch.Tensor       # int32 [nnz, 2]: column 0 doc id, column 1 fp32 weight bits — or, in the opt-in compressed
+    #                              format, int32 [nnz]: fp16 weight << 16 | block-local doc id (weight_format == "fp16")
     n_terms: int
     n_docs: int
     block_docs: int
+    weight_format: str = "fp32"
 
     @property
     def nnz(self):
@@ -130,25 +132,37 @@ class SparseDeviceIndex:
     def csr_arrays(self):
         """(term_offsets, doc_ids, weights) with lists in search order (a per-slice permutation of the canonical CSR)."""
         p = self.postings
+        if self.weight_format == "fp16":
+            raise NotImplementedError("csr_arrays of a compressed (fp16) index: doc ids are block-local there")
         return self.term_offsets, p[:, 0].contiguous(), p[:, 1].contiguous().view(torch.float32)
 
     @classmethod
-    def from_csr(cls, term_offsets, doc_ids, weights, n_docs, bank_order=True):
-        """Wrap a doc-sorted CSR: build the skip table and the search-side posting array (the CSR itself is only read)."""
+    def from_csr(cls, term_offsets, doc_ids, weights, n_docs, bank_order=True, weight_format="fp32"):
+        """Wrap a doc-sorted CSR: build the skip table and the search-side posting array (the CSR itself is only read).
+        `weight_format="fp16"` builds the opt-in compressed array (4 bytes per posting: fp16 weight + 16-bit block-local doc id);
+        searches over it score with the fp16-ROUNDED weights (see b200ret_sparse_layout_f16) — not the parity format."""
+        if weight_format not in ("fp32", "fp16"):
+            raise ValueError(f"weight_format must be 'fp32' or 'fp16', got {weight_format!r}")
         table = block_table_build(term_offsets, doc_ids, n_docs)
         n_terms = term_offsets.numel() - 1
         nnz = doc_ids.numel()
-        postings = torch.empty((nnz, 2), dtype=torch.int32, device=doc_ids.device)
+        lib = _lib.load()
         with torch.cuda.device(doc_ids.device):
-            _lib.check(_lib.load().b200ret_sparse_layout(_ptr(table), _ptr(doc_ids), _ptr(weights), nnz, n_terms, int(n_docs),
+            if weight_format == "fp32":
+                postings = torch.empty((nnz, 2), dtype=torch.int32, device=doc_ids.device)
+                _lib.check(lib.b200ret_sparse_layout(_ptr(table), _ptr(doc_ids), _ptr(weights), nnz, n_terms, int(n_docs),
+                                                     block_docs(), int(bool(bank_order)), _ptr(postings), _stream()))
+            else:
+                postings = torch.empty(nnz, dtype=torch.int32, device=doc_ids.device)
+                _lib.check(lib.b200ret_sparse_layout_f16(_ptr(table), _ptr(doc_ids), _ptr(weights), nnz, n_terms, int(n_docs),
                                                          block_docs(), int(bool(bank_order)), _ptr(postings), _stream()))
-        return cls(term_offsets, doc_ids, weights, table, postings, n_terms, int(n_docs), block_docs())
+        return cls(term_offsets, doc_ids, weights, table, postings, n_terms, int(n_docs), block_docs(), weight_format)
 
     @classmethod
-    def from_coo(cls, rows, cols, vals, n_terms, n_docs):
+    def from_coo(cls, rows, cols, vals, n_terms, n_docs, weight_format="fp32"):
         """Build from COO postings in any order (lists come out ascending in doc id)."""
         term_offsets, doc_ids, weights = csr_build(rows, cols, vals, n_terms, n_docs, sort_docs=True)
-        return cls.from_csr(term_offsets, doc_ids, weights, n_docs)
+        return cls.from_csr(term_offsets, doc_ids, weights, n_docs, weight_format=weight_format)
 
 
 def sparse_search(index, q_offsets, q_terms, q_weights, k, threshold=0.0, doc_id_base=0):
@@ -168,7 +182,8 @@ def sparse_search(index, q_offsets, q_terms, q_weights, k, threshold=0.0, doc_id
         out_counts = torch.empty(n_queries, dtype=torch.int32, device=dev)
         ws_bytes = lib.b200ret_sparse_search_workspace_bytes(n_queries, k)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        _lib.check(lib.b200ret_sparse_search(
+        entry = lib.b200ret_sparse_search_f16 if index.weight_format == "fp16" else lib.b200ret_sparse_search
+        _lib.check(entry(
             _ptr(index.table), _ptr(index.postings), index.n_terms, index.n_docs, index.block_docs,
             _ptr(q_offsets), _ptr(q_terms), _ptr(q_weights), n_queries, k, float(threshold), int(doc_id_base),
             _ptr(out_scores), _ptr(out_ids), _ptr(out_counts), _ptr(ws), ws_bytes, _stream()))
@@ -187,7 +202,8 @@ def sparse_scores(index, q_offsets, q_terms, q_weights):
     with torch.cuda.device(dev):
         out = torch.zeros((n_queries, n_blocks * index.block_docs), dtype=torch.float32, device=dev)
         ws = torch.empty(256, dtype=torch.uint8, device=dev)
-        _lib.check(lib.b200ret_sparse_scores(
+        entry = lib.b200ret_sparse_scores_f16 if index.weight_format == "fp16" else lib.b200ret_sparse_scores
+        _lib.check(entry(
             _ptr(index.table), _ptr(index.postings), index.n_terms, index.n_docs, index.block_docs,
             _ptr(q_offsets), _ptr(q_terms), _ptr(q_weights), n_queries, _ptr(out), _ptr(ws), 256, _stream()))
     return out[:, :index.n_docs]

@@ -313,3 +313,32 @@ def test_search_item_range_chunking(cuda, monkeypatch):
     dense_ref = ops.sparse_scores(index, q_off, q_t, q_w)
     monkeypatch.delenv("B200RET_TEST_MAX_ITEMS")
     assert torch.equal(dense_ref, ops.sparse_scores(index, q_off, q_t, q_w))
+
+
+@pytest.mark.parametrize("n_docs,n_terms,nq,k", [(30011, 2500, 120, 100), (ops.block_docs() * 3 + 1, 300, 33, 1000)])
+def test_fp16_weight_index_matches_oracle_on_rounded_weights(cuda, n_docs, n_terms, nq, k):
+    """The opt-in compressed posting format (north_star allows fp16 weights): 4-byte postings {fp16 weight,
+    block-local doc id}.  Its parity mode is the oracle run on the fp16-ROUNDED weights: all N scores and the top-k rows must be
+    bit-identical to that; against the fp32-weight scores the error stays within fp16 rounding (2^-11 relative per term)."""
+    rows, cols, vals = synth.gen_sparse_docs(n_docs, n_terms=n_terms, mean_nnz=40, seed=31, device=cuda)
+    q_off, q_t, q_w = synth.gen_sparse_queries(nq, n_terms=n_terms, mean_nnz=15, seed=32, device=cuda)
+    off, ids, w = ops.csr_build(rows, cols, vals, n_terms, n_docs)
+    index16 = ops.SparseDeviceIndex.from_csr(off, ids, w, n_docs, weight_format="fp16")
+    assert index16.postings.shape == (ids.numel(),) and index16.postings.element_size() == 4      # 4 bytes per posting
+    index32 = ops.SparseDeviceIndex.from_csr(off, ids, w, n_docs)
+    w16 = w.cpu().numpy().astype(np.float16).astype(np.float32)                                    # round-to-nearest-even, like the kernel
+    h_off, h_ids = off.cpu().numpy(), ids.cpu().numpy()
+    hq_off, hq_t, hq_w = q_off.cpu().numpy(), q_t.cpu().numpy(), q_w.cpu().numpy()
+
+    full = ops.sparse_scores(index16, q_off, q_t, q_w).cpu().numpy()
+    for qi in (0, nq // 2, nq - 1):
+        ref = c_oracle.sparse_scores(h_off, h_ids, w16, n_docs, hq_t[hq_off[qi]:hq_off[qi + 1]], hq_w[hq_off[qi]:hq_off[qi + 1]])
+        assert np.array_equal(full[qi].view(np.uint32), ref.view(np.uint32))
+    s16, i16, c16 = (x.cpu().numpy() for x in ops.sparse_search(index16, q_off, q_t, q_w, k, 0.0))
+    o_s, o_i, o_c = c_oracle.sparse_search(h_off, h_ids, w16, n_docs, hq_off, hq_t, hq_w, k)
+    assert np.array_equal(c16, o_c) and np.array_equal(i16, o_i) and np.array_equal(s16.view(np.uint32), o_s.view(np.uint32))
+
+    full32 = ops.sparse_scores(index32, q_off, q_t, q_w).cpu().numpy()
+    np.testing.assert_allclose(full, full32, rtol=2.0 ** -10, atol=1e-6)
+    with pytest.raises(ValueError):
+        ops.SparseDeviceIndex.from_csr(off, ids, w, n_docs, weight_format="int8")

@@ -46,24 +46,41 @@ def main():
     batches = [1, 8, 64, 512, 4096]
 
     q_off_all, q_t_all, q_w_all = synth.gen_sparse_queries(4096, device=dev)
-    for n_docs in corpus_sizes:
-        rows, cols, vals = synth.gen_sparse_docs(n_docs, device=dev)
-        off, ids, w = ops.csr_build(rows, cols, vals, synth.LLAMA3_VOCAB, n_docs)
-        del rows, cols, vals
-        index = ops.SparseDeviceIndex.from_csr(off, ids, w, n_docs)
-        index.release_canonical()
-        del ids, w
-        torch.cuda.empty_cache()
+    sparse_sizes = corpus_sizes if args.quick else corpus_sizes + [20_000_000]
+    for n_docs in sparse_sizes:
+        # one search-side index per doc range of <= 10 M docs: the kernels address postings with 32-bit positions, so the
+        # 20 M-doc corpus (4.0 G postings) is held as two consecutive ranges that are searched one after the other and merged
+        # (what IndexDictOfArray.device_shards does for a loaded index)
+        n_parts = (n_docs + 9_999_999) // 10_000_000
+        bounds = [(i * n_docs // n_parts, (i + 1) * n_docs // n_parts) for i in range(n_parts)]
+        parts, df = [], None
+        for lo, hi in bounds:
+            rows, cols, vals = synth.gen_sparse_docs(n_docs, device=dev, doc_lo=lo, doc_hi=hi)
+            rows -= lo
+            off, ids, w = ops.csr_build(rows, cols, vals, synth.LLAMA3_VOCAB, hi - lo)
+            del rows, cols, vals
+            index = ops.SparseDeviceIndex.from_csr(off, ids, w, hi - lo)
+            index.release_canonical()
+            del ids, w
+            torch.cuda.empty_cache()
+            parts.append((index, lo))
+            df = off if df is None else df + off
         for b in batches:
             q_off = q_off_all[:b + 1].contiguous()
             nq_terms = int(q_off[-1].item())
             q_t, q_w = q_t_all[:nq_terms].contiguous(), q_w_all[:nq_terms].contiguous()
-            ms = timed(lambda: ops.sparse_search(index, q_off, q_t, q_w, K, 0.0), 3 if b >= 512 else 5)
-            algo, postings = synth.sparse_algorithmic_bytes(off, q_t, b, K)
+
+            def search():
+                out = [ops.sparse_search(index, q_off, q_t, q_w, K, 0.0, doc_id_base=lo) for index, lo in parts]
+                if len(out) == 1:
+                    return out[0]
+                return ops.merge_topk(torch.stack([o[0] for o in out]), torch.stack([o[1] for o in out]), K)
+            ms = timed(search, 3 if b >= 512 else 5)
+            algo, postings = synth.sparse_algorithmic_bytes(df, q_t, b, K)
             print(json.dumps({"path": "sparse", "n_docs": n_docs, "batch": b, "ms": ms, "qps": b / ms * 1e3,
                               "algorithmic_gbs": algo / ms / 1e6, "frac_hbm": algo / ms / 1e6 / hbm,
-                              "postings_per_query": postings / b}), flush=True)
-        del index
+                              "postings_per_query": postings / b, "doc_ranges": n_parts}), flush=True)
+        del parts, index
         torch.cuda.empty_cache()
 
     dense_sizes = corpus_sizes if args.quick else corpus_sizes + [20_000_000]

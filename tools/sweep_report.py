@@ -14,8 +14,9 @@ def main(path):
     for p in pts:
         if p["path"] == "sparse":
             print("| {:,} | {} | {:.2f} | {:,.0f} | {:.3f} |".format(p["n_docs"], p["batch"], p["ms"], p["qps"], p["frac_hbm"]))
-    print("\nSmall batches are launch/latency bound (6 score + 6 select launches per call); the kernel needs a few hundred queries "
-          "to fill 148 SMs x 16 warps.\n")
+    print("\nSmall batches are launch/latency bound (7 score + 7 select launches per call); the kernel needs a few hundred queries "
+          "to fill 148 SMs x 15 warps.  The 20 M-doc corpus (4.0 G postings, beyond the kernels' 32-bit posting positions) is held as "
+          "two consecutive doc-range indexes on the one GPU, searched one after the other and merged (`merge_topk`).\n")
     print("## Dense (bf16, fp32 accumulate) — fraction of the bf16 tensor peak (2*Q*N*d FLOP) and of the HBM roof (corpus bytes N*d*2 per pass)\n")
     print("| dim | docs | batch | ms | QPS | frac of tensor peak | frac of HBM roof | bound |\n|---:|---:|---:|---:|---:|---:|---:|---|")
     for p in pts:
