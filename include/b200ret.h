@@ -258,6 +258,10 @@ int b200ret_write_run_json(const char* path_host, const int64_t* ids_host, const
                            const char* docid_blob_host, const int64_t* docid_offsets_host,
                            const int64_t* docid_ints_host, int64_t n_doc_ids, int64_t* bytes_written_host);
 
+/* Host helper: multi-threaded memcpy of result rows out of the reusable pinned staging buffers into caller-owned arrays
+ * (n_threads <= 0: 8). */
+int b200ret_host_copy(void* dst_host, const void* src_host, size_t bytes, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,7 @@ PROTOTYPES = {
     "b200ret_term_scores": (_c_int, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_ptr, _c_ptr]),
     "b200ret_rank_metrics": (_c_int, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr, _c_i32, ctypes.POINTER(_c_i32), _c_i32,
                                       _c_ptr, _c_ptr, _c_ptr]),
+    "b200ret_host_copy": (_c_int, [_c_ptr, _c_ptr, _c_sz, _c_int]),
     "b200ret_write_run_json": (_c_int, [ctypes.c_char_p, _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_ptr, _c_ptr,
                                         _c_ptr, _c_ptr, _c_ptr, _c_i64, ctypes.POINTER(_c_i64)]),
 }

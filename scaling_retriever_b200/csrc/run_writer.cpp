@@ -8,6 +8,9 @@
 // distinct and the external ids of one row are distinct (the Python caller checks both and otherwise takes the dict path).
 //
 // Host code only (no device work): queries are formatted in parallel (OpenMP) into per-chunk buffers and written in order.
+#include <omp.h>
+
+#include <algorithm>
 #include <charconv>
 #include <cmath>
 #include <cstdint>
@@ -165,7 +168,9 @@ extern "C" int b200ret_write_run_json(const char* path_host, const int64_t* ids_
     std::vector<std::string> chunks(static_cast<size_t>(n_chunks));
     std::vector<int> chunk_live(static_cast<size_t>(n_chunks), 0);
     int bad = 0;
-#pragma omp parallel for schedule(dynamic, 1)
+    // explicit team size: torch.distributed.run exports OMP_NUM_THREADS=1 to every rank, and only the first worker formats a run
+    const int n_threads = std::max(1, std::min(omp_get_num_procs(), 32));
+#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads)
     for (int ch = 0; ch < n_chunks; ++ch) {
         const int32_t q0 = static_cast<int32_t>(static_cast<int64_t>(n_queries) * ch / n_chunks);
         const int32_t q1 = static_cast<int32_t>(static_cast<int64_t>(n_queries) * (ch + 1) / n_chunks);
@@ -238,5 +243,23 @@ extern "C" int b200ret_write_run_json(const char* path_host, const int64_t* ids_
         return B200RET_EINVAL;
     }
     if (bytes_written_host) *bytes_written_host = total;
+    return B200RET_OK;
+}
+
+// Parallel host memcpy (result rows out of the reusable pinned staging buffers into arrays the caller owns): a fresh 84 MB
+// destination is page-faulted in by several threads instead of one.
+extern "C" int b200ret_host_copy(void* dst_host, const void* src_host, size_t bytes, int n_threads) {
+    if (bytes == 0) return B200RET_OK;
+    if (!dst_host || !src_host) {
+        b200ret::set_err("host_copy: null pointer");
+        return B200RET_EINVAL;
+    }
+    const int n = std::max(1, std::min({n_threads > 0 ? n_threads : 8, omp_get_num_procs(), static_cast<int>(bytes / (1 << 20)) + 1}));
+    const size_t part = (bytes / n + 4095) & ~static_cast<size_t>(4095);
+#pragma omp parallel for schedule(static, 1) num_threads(n)
+    for (int t = 0; t < n; ++t) {
+        const size_t a = std::min(bytes, part * t), b = std::min(bytes, part * (t + 1));
+        if (b > a) memcpy(static_cast<char*>(dst_host) + a, static_cast<const char*>(src_host) + a, b - a);
+    }
     return B200RET_OK;
 }

@@ -24,7 +24,7 @@ from tqdm import tqdm
 
 from . import ops, shard
 from .inverted_index import MAX_SHARD_POSTINGS, IndexDictOfArray
-from .results import ExternalIds, IdRows, LazyRun
+from .results import ExternalIds, IdRows, LazyRun, owned_copy
 from .utils import is_first_worker, obtain_doc_vec_dir_files, rank as _rank, supports_bfloat16, to_list, world_size as _world_size
 
 logger = logging.getLogger()
@@ -389,8 +389,8 @@ class DenseFlatIndexer(DenseIndexer):
         scores, indexes = self.search_arrays(query_reps, top_docs)
         # reference indexer.py:212: [[index_id_to_db_id[idx] ...]] (a -1 label indexes the last id there; kept identical) as a
         # sequence of rows gathered on access (results.IdRows) instead of Q*k eager Python list lookups
-        top_doc_ids = IdRows(self.external_ids(), indexes.copy())
-        return top_doc_ids, scores.copy()   # search_arrays returns views of reusable pinned staging buffers
+        top_doc_ids = IdRows(self.external_ids(), owned_copy(indexes))
+        return top_doc_ids, owned_copy(scores)   # search_arrays returns views of reusable pinned staging buffers
 
     def external_ids(self):
         if self._ext is None or self._ext.size != len(self.index_id_to_db_id):
@@ -494,14 +494,16 @@ class SparseIndexer:
 
 def pack_queries(sparse_query_vecs):
     """list of (col int32[nnz], values fp32[nnz]) (indexer.py:400-401) -> CSR-packed host arrays."""
-    q_offsets = np.zeros(len(sparse_query_vecs) + 1, dtype=np.int32)
-    if sparse_query_vecs:
-        q_offsets[1:] = np.cumsum([len(c) for c, _ in sparse_query_vecs])
-        q_terms = np.concatenate([np.asarray(c, dtype=np.int32) for c, _ in sparse_query_vecs]) if q_offsets[-1] else np.zeros(0, np.int32)
-        q_weights = np.concatenate([np.asarray(v, dtype=np.float32) for _, v in sparse_query_vecs]) if q_offsets[-1] else np.zeros(0, np.float32)
+    n = len(sparse_query_vecs)
+    q_offsets = np.zeros(n + 1, dtype=np.int32)
+    if n:
+        np.cumsum(np.fromiter((len(c) for c, _ in sparse_query_vecs), dtype=np.int64, count=n), out=q_offsets[1:])
+    if n and q_offsets[-1]:
+        q_terms = np.concatenate([c for c, _ in sparse_query_vecs]).astype(np.int32, copy=False)
+        q_weights = np.concatenate([v for _, v in sparse_query_vecs]).astype(np.float32, copy=False)
     else:
         q_terms, q_weights = np.zeros(0, np.int32), np.zeros(0, np.float32)
-    return q_offsets, q_terms.astype(np.int32, copy=False), q_weights.astype(np.float32, copy=False)
+    return q_offsets, q_terms, q_weights
 
 
 class SparseRetrieval:
@@ -701,7 +703,7 @@ class SparseRetrieval:
         if scores is None:
             res = LazyRun([], np.zeros((0, topk), np.int64), np.zeros((0, topk), np.float32), np.zeros(0, np.int32), self._external_ids())
         else:   # search_arrays hands out views of reusable pinned staging buffers: the run owns copies
-            res = LazyRun(qids, np.array(ids), np.array(scores), np.array(counts), self._external_ids())
+            res = LazyRun(qids, owned_copy(ids), owned_copy(scores), np.array(counts), self._external_ids())
         stats = defaultdict(float)
         for n in np.diff(q_offsets).tolist():
             stats["L0_q"] += n / len(qids)
@@ -954,7 +956,7 @@ class HybridRetriever:
         last id like the reference's list indexing, :212)."""
         assert len(qids) == len(query_reps), (len(qids), len(query_reps))
         scores, indexes = self.dense_index.search_arrays(query_reps, topk)
-        return LazyRun(qids, np.array(indexes), np.array(scores), None, self.dense_index.external_ids())
+        return LazyRun(qids, owned_copy(indexes), owned_copy(scores), None, self.dense_index.external_ids())
 
     def _sparse_retrieve(self, sparse_query_vecs, qids, threshold=0., topk=1000):
         return self.sparse._sparse_retrieve_multithreaded(sparse_query_vecs, qids, threshold=threshold, topk=topk)

@@ -18,6 +18,17 @@ import numpy as np
 from . import _lib
 
 
+def owned_copy(arr):
+    """A caller-owned copy of a (pinned staging) result array, made by several host threads."""
+    arr = np.ascontiguousarray(arr)
+    out = np.empty_like(arr)
+    if arr.nbytes < (4 << 20):
+        out[...] = arr
+    else:
+        _lib.check(_lib.load().b200ret_host_copy(ctypes.c_void_p(out.ctypes.data), ctypes.c_void_p(arr.ctypes.data), arr.nbytes, 8))
+    return out
+
+
 class ExternalIds:
     """Row label -> external id table (`doc_ids.pkl` dict / list, `index_id_to_db_id` list, or a range), in the forms the
     lazy run and the native writer need.  Everything is built on first use and cached."""

@@ -21,7 +21,8 @@ def main(src, dst, steps):
     per = defaultdict(lambda: defaultdict(float))
     for r in rows[1:]:
         try:
-            per[r[ki].split("(")[0]][(int(r[ii]), r[mi])] = float(r[vi].replace(",", ""))
+            name = r[ki].split("(")[0].replace("void ", "").split("<")[0]        # template instances count under the kernel's name
+            per[name][(int(r[ii]), r[mi])] = float(r[vi].replace(",", ""))
         except ValueError:
             continue
     from scaling_retriever_b200 import _lib
