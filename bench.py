@@ -562,7 +562,7 @@ def bench_dense(args, ctx, dim):
         assert np.array_equal(e_out[1], out[1].cpu().numpy())
         d2h = int(e_out[0].nbytes + e_out[1].nbytes)
 
-    # the reference-facing method: search_knn(query_reps fp32 [Q, d], top_docs) -> (list[list[db id]], fp32 [Q, k]) on every rank
+    # the reference-facing method: search_knn(query_reps fp32 [Q, d], top_docs) -> (rows of db ids, fp32 [Q, k]) on the first worker
     api_steps = max(1, min(args.steps, 3))
     api_s, api_out = ctx.time_wall(lambda: index.search_knn(h_q, K_TOP), api_steps, warmup=1)
     if rank == 0:

@@ -386,7 +386,12 @@ class DenseFlatIndexer(DenseIndexer):
             return out_s.numpy(), out_i.numpy()
 
     def search_knn(self, query_reps: np.array, top_docs: int):
-        scores, indexes = self.search_arrays(query_reps, top_docs)
+        """reference indexer.py:210-214.  Sharded (torchrun, world_size > 1): like retrieve() on the sparse side, the merged rows
+        are delivered to the FIRST worker only (each GPU copies its query slice into host rows shared with it); the other ranks
+        get zero rows."""
+        scores, indexes = self.search_arrays(query_reps, top_docs, host_ranks="first")
+        if scores is None:
+            return IdRows(self.external_ids(), np.zeros((0, int(top_docs)), np.int64)), np.zeros((0, int(top_docs)), np.float32)
         # reference indexer.py:212: [[index_id_to_db_id[idx] ...]] (a -1 label indexes the last id there; kept identical) as a
         # sequence of rows gathered on access (results.IdRows) instead of Q*k eager Python list lookups
         top_doc_ids = IdRows(self.external_ids(), owned_copy(indexes))
@@ -955,7 +960,9 @@ class HybridRetriever:
         """reference indexer.py:973-982; the run is a LazyRun over the [Q, k] arrays (rows padded with label -1 map to the
         last id like the reference's list indexing, :212)."""
         assert len(qids) == len(query_reps), (len(qids), len(query_reps))
-        scores, indexes = self.dense_index.search_arrays(query_reps, topk)
+        scores, indexes = self.dense_index.search_arrays(query_reps, topk, host_ranks="first")
+        if scores is None:     # sharded search: the run lives on the first worker (the rank that writes dense/run.json)
+            return LazyRun([], np.zeros((0, topk), np.int64), np.zeros((0, topk), np.float32), None, self.dense_index.external_ids())
         return LazyRun(qids, owned_copy(indexes), owned_copy(scores), None, self.dense_index.external_ids())
 
     def _sparse_retrieve(self, sparse_query_vecs, qids, threshold=0., topk=1000):

@@ -82,7 +82,12 @@ def main():
     flat.index_data(docs.float().cpu().numpy(), [f"P{j}" for j in range(nd)])
     assert flat.index.shape[0] == hi - lo
     top_ids, top_scores = flat.search_knn(queries.cpu().numpy(), kd)
-    assert top_ids[5][0] == f"P{int(ref_i[5, 0])}" and np.array_equal(top_scores, ref_s.cpu().numpy())
+    if rank == 0:          # like the sparse run: the merged rows are delivered to the first worker
+        assert top_ids[5][0] == f"P{int(ref_i[5, 0])}" and np.array_equal(top_scores, ref_s.cpu().numpy())
+    else:
+        assert len(top_ids) == 0 and top_scores.shape == (0, kd)
+    full_s, full_i = flat.search_arrays(queries.cpu().numpy(), kd)          # host_ranks="all": every rank gets every row
+    assert np.array_equal(full_i, ref_i.cpu().numpy()) and np.array_equal(full_s, ref_s.cpu().numpy())
     d1 = flat.search_arrays(queries.cpu().numpy(), kd, host_ranks="first")
     if rank == 0:
         assert np.array_equal(d1[1], ref_i.cpu().numpy()) and np.array_equal(d1[0], ref_s.cpu().numpy())

@@ -118,3 +118,20 @@ def test_dense_search_matches_exact_construction_golden(cuda):
     parts = [ops.dense_search(docs[a:b].contiguous(), queries, k, doc_id_base=a) for a, b in zip(bounds[:-1], bounds[1:])]
     ms, mi, _ = ops.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), k)
     assert np.array_equal(mi.cpu().numpy(), g["top_ids"]) and np.array_equal(ms.cpu().numpy().view(np.uint32), g["top_scores"].view(np.uint32))
+
+
+def test_dense_search_large_k(cuda):
+    """k = 4096 (B200RET_MAX_K): candidate capacity k + 5 k; exact-construction style inputs so ids and scores are bit-exact."""
+    g = torch.Generator().manual_seed(9)
+    n, d, nq, k = 30000, 64, 16, 4096
+    docs = torch.randint(-1, 2, (n, d), generator=g).float()
+    ids = torch.arange(n)
+    docs[:, d - 2] = (ids % 256).float()
+    docs[:, d - 1] = (ids // 256).float()
+    qs = torch.randint(-1, 2, (nq, d), generator=g).float()
+    qs[:, d - 2] = 2.0 ** -16
+    qs[:, d - 1] = 2.0 ** -8
+    s, i, c = ops.dense_search(ops.f32_to_bf16(docs.to(cuda)), ops.f32_to_bf16(qs.to(cuda)), k)
+    o_s, o_i = dense_oracle.flat_ip_search(docs.numpy(), qs.numpy(), k)
+    assert np.array_equal(i.cpu().numpy(), o_i) and np.array_equal(s.cpu().numpy().view(np.uint32), o_s.view(np.uint32))
+    assert (c.cpu().numpy() == k).all()

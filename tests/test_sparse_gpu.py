@@ -342,3 +342,65 @@ def test_fp16_weight_index_matches_oracle_on_rounded_weights(cuda, n_docs, n_ter
     np.testing.assert_allclose(full, full32, rtol=2.0 ** -10, atol=1e-6)
     with pytest.raises(ValueError):
         ops.SparseDeviceIndex.from_csr(off, ids, w, n_docs, weight_format="int8")
+
+
+def test_search_large_k_capacity(cuda):
+    """k = 4096 (B200RET_MAX_K): the candidate capacity is k + 5 k there (with k + 2 blocks almost every query
+    overflowed every round and the whole batch was re-run under the safe schedule) — results vs the oracle, and no query may
+    need the safe re-run on exchangeable data (the launch count equals one geometric schedule)."""
+    n_docs, n_terms, nq, k = 90000, 3000, 24, 4096
+    rows, cols, vals = synth.gen_sparse_docs(n_docs, n_terms=n_terms, mean_nnz=60, seed=41, device=cuda)
+    q_off, q_t, q_w = synth.gen_sparse_queries(nq, n_terms=n_terms, mean_nnz=25, seed=42, device=cuda)
+    off, ids, w = ops.csr_build(rows, cols, vals, n_terms, n_docs)
+    index = ops.SparseDeviceIndex.from_csr(off, ids, w, n_docs)
+    ops.profile_enable(True)
+    ops.profile_read(ops.PROF_SPARSE_SCORE)
+    s, i, c = ops.sparse_search(index, q_off, q_t, q_w, k, 0.0)
+    _, score_launches, _ = ops.profile_read(ops.PROF_SPARSE_SCORE)
+    ops.profile_enable(False)
+    o_s, o_i, o_c = c_oracle.sparse_search(off.cpu().numpy(), ids.cpu().numpy(), w.cpu().numpy(), n_docs, q_off.cpu().numpy(),
+                                           q_t.cpu().numpy(), q_w.cpu().numpy(), k)
+    assert np.array_equal(c.cpu().numpy(), o_c) and np.array_equal(i.cpu().numpy(), o_i)
+    assert np.array_equal(s.cpu().numpy().view(np.uint32), o_s.view(np.uint32))
+    n_blocks = (n_docs + ops.block_docs() - 1) // ops.block_docs()
+    rounds, seen, size = 0, 0, 2
+    while seen < n_blocks:                       # the geometric schedule of candidates.cuh (2 blocks, then 3x the docs seen)
+        seen = n_blocks if n_blocks - seen <= size else seen + size
+        size = seen * 3
+        rounds += 1
+    assert score_launches == rounds, (score_launches, rounds)
+
+
+def test_search_property_random_small_cases(cuda):
+    """Property test over many tiny random cases (SURVEY §8c list): empty queries, terms with empty lists, k > hits, positive and
+    negative thresholds, doc counts that are no multiple of any tile, k from 1 to 300 — every row must equal the oracle's."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None, derandomize=True)
+    @given(seed=st.integers(0, 10 ** 6), n_docs=st.integers(1, 9000), n_terms=st.integers(1, 400), nq=st.integers(1, 12),
+           k=st.integers(1, 300), threshold=st.sampled_from([0.0, 0.0, 0.7, 2.5, -1.0]))
+    def check(seed, n_docs, n_terms, nq, k, threshold):
+        rng = np.random.default_rng(seed)
+        nnz = int(rng.integers(0, 6 * n_docs + 1))
+        pairs = np.unique(np.stack([rng.integers(0, n_docs, nnz), rng.integers(0, n_terms, nnz)], axis=1), axis=0) if nnz else np.zeros((0, 2), np.int64)
+        rows, cols = pairs[:, 0].astype(np.int32), pairs[:, 1].astype(np.int32)
+        vals = (rng.random(len(rows)) * 2 + 1e-3).astype(np.float32)
+        q_terms, q_off = [], [0]
+        for _ in range(nq):
+            t = np.sort(rng.choice(n_terms, size=int(rng.integers(0, min(n_terms, 20) + 1)), replace=False))
+            q_terms.append(t)
+            q_off.append(q_off[-1] + len(t))
+        q_t = np.concatenate(q_terms).astype(np.int32) if q_off[-1] else np.zeros(0, np.int32)
+        q_w = (rng.random(len(q_t)) * 2 + 1e-3).astype(np.float32)
+        q_off = np.asarray(q_off, dtype=np.int32)
+        index = ops.SparseDeviceIndex.from_coo(torch.as_tensor(rows).to(cuda), torch.as_tensor(cols).to(cuda), torch.as_tensor(vals).to(cuda),
+                                               n_terms, n_docs)
+        s, i, c = ops.sparse_search(index, torch.as_tensor(q_off).to(cuda), torch.as_tensor(q_t).to(cuda), torch.as_tensor(q_w).to(cuda),
+                                    k, threshold)
+        o_off, o_ids, o_w = c_oracle.build_csr(rows, cols, vals, n_terms)
+        o_s, o_i, o_c = c_oracle.sparse_search(o_off, o_ids, o_w, n_docs, q_off, q_t, q_w, k, threshold)
+        assert np.array_equal(c.cpu().numpy(), o_c)
+        assert np.array_equal(i.cpu().numpy(), o_i)
+        assert np.array_equal(s.cpu().numpy().view(np.uint32), o_s.view(np.uint32))
+
+    check()
