@@ -26,7 +26,13 @@ namespace b200ret {
 constexpr int D_BLOCK_M = 128;             // query rows per CTA (256 per pair)
 constexpr int D_BLOCK_N = 256;             // doc rows per pair tile (128 loaded by each CTA)
 constexpr int D_BLOCK_K = 64;              // bf16 elements per K block = 128 bytes = one swizzle atom row
-constexpr int D_STAGES = 6;
+#ifndef B200RET_DENSE_STAGES
+#define B200RET_DENSE_STAGES 6
+#endif
+#ifndef B200RET_DENSE_EPI_PIPE          // 1 = the epilogue's maximum pass keeps two tcgen05.ld in flight per wait
+#define B200RET_DENSE_EPI_PIPE 1
+#endif
+constexpr int D_STAGES = B200RET_DENSE_STAGES;
 constexpr int D_THREADS = 256;
 constexpr int D_TMEM_COLS = 512;           // 2 accumulator stages x 256 fp32 columns
 constexpr uint32_t D_TILE_BYTES = 128 * D_BLOCK_K * 2;            // one 128-row operand tile: 16 KB
@@ -155,6 +161,28 @@ __device__ __forceinline__ void tmem_load_32cols(uint32_t taddr, uint32_t (&v)[3
         : "memory");
 }
 
+// two 32-column loads in flight, one wait
+__device__ __forceinline__ void tmem_load_2x32cols(uint32_t taddr0, uint32_t taddr1, uint32_t (&a)[32], uint32_t (&b)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%64];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%65];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]), "=r"(a[9]),
+          "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]), "=r"(a[16]), "=r"(a[17]), "=r"(a[18]),
+          "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]), "=r"(a[24]), "=r"(a[25]), "=r"(a[26]), "=r"(a[27]),
+          "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31]),
+          "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]), "=r"(b[8]), "=r"(b[9]),
+          "=r"(b[10]), "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]), "=r"(b[15]), "=r"(b[16]), "=r"(b[17]), "=r"(b[18]),
+          "=r"(b[19]), "=r"(b[20]), "=r"(b[21]), "=r"(b[22]), "=r"(b[23]), "=r"(b[24]), "=r"(b[25]), "=r"(b[26]), "=r"(b[27]),
+          "=r"(b[28]), "=r"(b[29]), "=r"(b[30]), "=r"(b[31])
+        : "r"(taddr0), "r"(taddr1)
+        : "memory");
+}
+
 // ---- the kernel -----------------------------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D_THREADS, 1)
 dense_search_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_d, const DenseParams p) {
@@ -256,6 +284,18 @@ dense_search_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             // tau still low in the first rounds a tile's epilogue took 20x its MMA time — a fixed cost per shard that
             // dominated small shards.)  tcgen05.ld is warp-collective, so the extra passes are taken warp-uniformly.
             bool any = false;
+#if B200RET_DENSE_EPI_PIPE
+#pragma unroll 1
+            for (int c = 0; c < D_BLOCK_N / 32; c += 2) {
+                uint32_t v[32], u[32];
+                const uint32_t t0 = tmem_base + ((ew * 32u) << 16) + acc * D_BLOCK_N + c * 32;
+                tmem_load_2x32cols(t0, t0 + 32, v, u);
+                float m = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) m = fmaxf(m, fmaxf(__uint_as_float(v[j]), __uint_as_float(u[j])));
+                any |= m > tq;
+            }
+#else
 #pragma unroll 1
             for (int c = 0; c < D_BLOCK_N / 32; ++c) {
                 uint32_t v[32];
@@ -265,6 +305,7 @@ dense_search_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
                 any |= m > tq;
             }
+#endif
             if (__any_sync(0xffffffffu, any)) {
                 const int32_t live_cols = p.doc_end - doc0;      // columns >= live_cols are past the end of the shard
                 int cnt = 0;
