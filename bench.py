@@ -201,8 +201,8 @@ def sparse_sizes(args):
 
 
 def parallelism(n_gpus):
-    return (f"doc-range shards x{n_gpus}, packed-key all-to-all + per-slice merge + all-gather over NCCL; queries replicated"
-            if n_gpus > 1 else "1 GPU")
+    return (f"doc-range shards x{n_gpus}, per-round MIN all-reduce of the shards' bounds, packed-key all-to-all + per-slice merge + "
+            "all-gather over NCCL; queries replicated" if n_gpus > 1 else "1 GPU")
 
 
 L2_NOTE = "inputs larger than L2 (index / corpus of several GB vs 126 MB L2), no flush"
@@ -342,8 +342,11 @@ def bench_sparse(args, ctx):
     algo_bytes, postings = synth.sparse_algorithmic_bytes(term_offsets, q_terms, n_queries, K_TOP,
                                                           weight_bytes=4 if args.sparse_weights == "fp32" else 2)
 
+    # N > 1: the shards exchange their bounds between the rounds (one 28 KB MIN all-reduce per round, shard.TauExchange)
+    exchange = shard.TauExchange("sparse", n_docs, dev) if (world > 1 and args.sparse_weights == "fp32" and not args.no_tau_exchange) else None
+
     def step():
-        s, i, c = ops.sparse_search(index, q_off, q_terms, q_w, K_TOP, 0.0, doc_id_base=lo)
+        s, i, c = ops.sparse_search(index, q_off, q_terms, q_w, K_TOP, 0.0, doc_id_base=lo, exchange=exchange)
         if world > 1:
             s, i, c = shard.merge_shards(s, i, K_TOP, n_docs_total=n_docs)
         return s, i, c
@@ -533,8 +536,10 @@ def bench_dense(args, ctx, dim):
     h_q = h_q_pin.numpy()
     flops = 2.0 * n_queries * (hi - lo) * dim
 
+    exchange = shard.TauExchange("dense", n_docs, dev) if (world > 1 and not args.no_tau_exchange) else None
+
     def step():
-        s, i, c = ops.dense_search(corpus, q16, K_TOP, doc_id_base=lo)
+        s, i, c = ops.dense_search(corpus, q16, K_TOP, doc_id_base=lo, exchange=exchange)
         if world > 1:
             s, i, c = shard.merge_shards(s, i, K_TOP, n_docs_total=n_docs)
         return s, i, c
@@ -721,6 +726,7 @@ def main():
     ap.add_argument("--n-docs", type=int, default=0, help="override the corpus size (debug; the headline is 8,841,823)")
     ap.add_argument("--n-queries", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tau-exchange", action="store_true", help="(N > 1, A/B only) shards do not exchange their bounds between rounds")
     ap.add_argument("--workload", default="both", choices=["both", "sparse", "dense"],
                     help="both (default) = sparse configs[1] at the top level + dense configs[2] (and configs[3] at N >= 8) as "
                          "sub-records; sparse / dense = that workload alone")

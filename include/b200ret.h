@@ -182,6 +182,43 @@ int b200ret_dense_search(const void* corpus_bf16, const void* queries_bf16,
 int b200ret_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * (3b) Sharded search with a tau exchange between the rounds.
+ * A doc-range sharded search runs the rounds of (2)/(3) on every shard.  Alone, a shard can only raise its bound tau[q] to
+ * ITS k-th best score, so every shard emits and selects as many candidates per round as a whole corpus would.  With the
+ * exchange, after every round each shard also publishes aux[q] = the score of its ceil(k / n_shards)-th best candidate so far
+ * (-inf if it has fewer); `hook` — provided by the host side, which owns the communicator — all-reduces aux with MIN over
+ * the shards on the search's stream, and tau[q] is raised to just below that minimum: every shard holds at least
+ * ceil(k / n_shards) documents at or above it, so at least k documents of the corpus do, and a document scoring strictly
+ * below it cannot be in the global top-k.  Results are exactly those of the plain entry points after the merge.
+ * `hook(user)` must ENQUEUE the all-reduce (no host synchronisation) and return 0; it is called exactly `n_exchanges` times
+ * per search on every shard (b200ret_*_exchange_rounds of the LARGEST shard), whatever the shard's own size.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t aux_rank;            /* ceil(k / n_shards) */
+    int32_t n_exchanges;         /* hook calls per search, the same on every shard */
+    float* aux;                  /* device [n_queries] */
+    int (*hook)(void* user);
+    void* user;
+} b200ret_round_exchange;
+
+int32_t b200ret_sparse_exchange_rounds(int32_t n_docs_largest_shard);
+int32_t b200ret_dense_exchange_rounds(int32_t n_docs_largest_shard);
+
+int b200ret_sparse_search_sharded(const uint32_t* table, const void* postings,
+                                  int32_t n_terms, int32_t n_docs, int32_t block_docs,
+                                  const int32_t* q_offsets, const int32_t* q_terms, const float* q_weights,
+                                  int32_t n_queries, int32_t k, float threshold, int64_t doc_id_base,
+                                  float* out_scores, int64_t* out_ids, int32_t* out_counts,
+                                  void* workspace, size_t workspace_bytes, void* stream,
+                                  const b200ret_round_exchange* exchange);
+
+int b200ret_dense_search_sharded(const void* corpus_bf16, const void* queries_bf16,
+                                 int32_t n_docs, int32_t n_queries, int32_t dim, int32_t k, int64_t doc_id_base,
+                                 float* out_scores, int64_t* out_ids, int32_t* out_counts,
+                                 void* workspace, size_t workspace_bytes, void* stream,
+                                 const b200ret_round_exchange* exchange);
+
+/* ------------------------------------------------------------------------------------------------
  * (4) Shard merge: G per-shard top-k lists (as produced above, gathered with an NCCL all-gather)
  * -> one global top-k per query under the same total order (score desc, doc id asc).
  * in_scores/in_ids: [G, n_queries, k] contiguous; shard g's ids are all smaller than shard g+1's (doc-range

@@ -62,7 +62,8 @@ template <bool FINAL>
 __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(uint64_t* cand, int32_t* cand_count, int32_t cap, int32_t k,
                                                                        float* tau, int32_t* overflow, int32_t n_queries,
                                                                        const int32_t* q_list, int64_t doc_id_base,
-                                                                       float* out_scores, int64_t* out_ids, int32_t* out_counts) {
+                                                                       float* out_scores, int64_t* out_ids, int32_t* out_counts,
+                                                                       int32_t aux_rank, float* aux) {
     extern __shared__ __align__(16) uint64_t skeys[];
     __shared__ uint32_t hist[256];
     __shared__ uint64_t bcast[3];
@@ -77,7 +78,12 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(uint64_t* cand, 
         }
         c = cap;
     }
-    if (!FINAL && c <= k) return;   // nothing to cut; tau keeps its value (block-uniform exit)
+    // tau exchange of a sharded search: this shard's aux_rank-th best score so far (-inf if it has fewer candidates)
+    const bool want_aux = !FINAL && aux != nullptr;
+    if (want_aux && c < aux_rank) {
+        if (threadIdx.x == 0) aux[q] = -INFINITY;
+    }
+    if (!FINAL && c <= k && !(want_aux && c >= aux_rank)) return;   // nothing to cut or publish (block-uniform exit)
 
     const int n_sort = FINAL ? next_pow2(max(min(c, k), 1)) : 0;
 #if B200RET_SELECT_BULK
@@ -99,6 +105,11 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(uint64_t* cand, 
     __syncthreads();
 #endif
     int kept = c;
+    if (want_aux && c >= aux_rank) {        // block-uniform; the keys in shared memory are only read by the selections
+        const uint64_t mth = block_radix_select_kth(skeys, c, aux_rank, hist, bcast);
+        if (threadIdx.x == 0) aux[q] = cand_score(mth);
+        __syncthreads();
+    }
     if (c > k) {
         const uint64_t kth = block_radix_select_kth(skeys, c, k, hist, bcast);
         // Compact the k winners to the front of the global list (their order there is irrelevant).
@@ -133,7 +144,7 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(uint64_t* cand, 
 // Launch helpers (host).  `prof_kind` brackets the select launches for bench.py.
 int launch_select(bool final, const CandBuffers& b, int32_t cap, int32_t k, int32_t n_queries, int32_t n_active,
                          const int32_t* q_list, int64_t doc_id_base, float* out_scores, int64_t* out_ids, int32_t* out_counts,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, int32_t aux_rank, float* aux) {
     const size_t smem = static_cast<size_t>(cap) * sizeof(uint64_t);
     static PerDeviceOnce attrs_set;
     if (attrs_set.first()) {
@@ -148,16 +159,44 @@ int launch_select(bool final, const CandBuffers& b, int32_t cap, int32_t k, int3
     prof_begin(PROF_SPARSE_SELECT, stream);
     if (final)
         select_kernel<true><<<n_active, SELECT_THREADS, smem, stream>>>(b.cand, b.cand_count, cap, k, b.tau, b.overflow, n_queries,
-                                                                      q_list, doc_id_base, out_scores, out_ids, out_counts);
+                                                                      q_list, doc_id_base, out_scores, out_ids, out_counts, 0, nullptr);
     else
         select_kernel<false><<<n_active, SELECT_THREADS, smem, stream>>>(b.cand, b.cand_count, cap, k, b.tau, b.overflow, n_queries,
-                                                                       q_list, doc_id_base, nullptr, nullptr, nullptr);
+                                                                       q_list, doc_id_base, nullptr, nullptr, nullptr, aux_rank, aux);
     prof_end(PROF_SPARSE_SELECT, stream);
     count_launches(1);
     B200RET_CUDA_CHECK(cudaGetLastError());
     return B200RET_OK;
 }
 
+
+__global__ void aux_init_kernel(float* aux, int32_t n_queries) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_queries) aux[i] = -INFINITY;
+}
+
+// tau <- max(tau, largest float below aux): documents scoring EXACTLY the exchanged bound stay eligible (a tie with a
+// document of another shard is decided by the doc id, which this shard cannot judge)
+__global__ void tau_raise_kernel(float* tau, const float* aux, int32_t n_queries) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_queries) return;
+    const float a = aux[i];
+    if (a > -INFINITY && a == a) tau[i] = fmaxf(tau[i], nextafterf(a, -INFINITY));
+}
+
+int launch_aux_init(float* aux, int32_t n_queries, cudaStream_t stream) {
+    aux_init_kernel<<<(n_queries + 255) / 256, 256, 0, stream>>>(aux, n_queries);
+    count_launches(1);
+    B200RET_CUDA_CHECK(cudaGetLastError());
+    return B200RET_OK;
+}
+
+int launch_tau_raise(float* tau, const float* aux, int32_t n_queries, cudaStream_t stream) {
+    tau_raise_kernel<<<(n_queries + 255) / 256, 256, 0, stream>>>(tau, aux, n_queries);
+    count_launches(1);
+    B200RET_CUDA_CHECK(cudaGetLastError());
+    return B200RET_OK;
+}
 
 int launch_cand_init(const CandBuffers& b, int32_t n_queries, float threshold, cudaStream_t stream) {
     cand_init_kernel<<<(n_queries + 255) / 256, 256, 0, stream>>>(b.tau, b.cand_count, b.overflow, n_queries, threshold);

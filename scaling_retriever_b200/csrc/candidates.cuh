@@ -45,6 +45,18 @@ inline size_t carve_cand(Workspace& ws, int32_t n_queries, int32_t cap, CandBuff
     return ws.used;
 }
 
+// Non-final round count of the geometric schedule (= select launches between rounds) for `n_units` units.
+inline int32_t schedule_exchanges(int32_t n_units, int32_t round0_units) {
+    int32_t unit = 0, size = round0_units, selects = 0;
+    while (unit < n_units) {
+        const int32_t end = (n_units - unit <= size) ? n_units : unit + size;
+        if (end < n_units) ++selects;
+        unit = end;
+        size = unit * (ROUND_GROWTH - 1);
+    }
+    return selects;
+}
+
 // Kernels + launchers live in candidates.cu (one definition for both searches).
 int launch_cand_init(const CandBuffers& b, int32_t n_queries, float threshold, cudaStream_t stream);
 int launch_cand_rearm(const CandBuffers& b, int32_t n_queries, float threshold, cudaStream_t stream);
@@ -52,7 +64,10 @@ int launch_cand_rearm(const CandBuffers& b, int32_t n_queries, float threshold, 
 // and writes the output row (ids + doc_id_base, tail padded with (-inf, -1)).
 int launch_select(bool final, const CandBuffers& b, int32_t cap, int32_t k, int32_t n_queries, int32_t n_active,
                   const int32_t* q_list, int64_t doc_id_base, float* out_scores, int64_t* out_ids, int32_t* out_counts,
-                  cudaStream_t stream);
+                  cudaStream_t stream, int32_t aux_rank = 0, float* aux = nullptr);
+// tau exchange of a sharded search (b200ret_round_exchange): aux <- -inf; after the hook: tau <- max(tau, just below aux)
+int launch_aux_init(float* aux, int32_t n_queries, cudaStream_t stream);
+int launch_tau_raise(float* tau, const float* aux, int32_t n_queries, cudaStream_t stream);
 
 // Round driver shared by both searches.  `launch_round(unit_begin, unit_end, q_list, n_active)` scores the doc units
 // [unit_begin, unit_end) for the active queries and appends candidates; a "unit" is a fixed number of documents
@@ -60,20 +75,41 @@ int launch_select(bool final, const CandBuffers& b, int32_t cap, int32_t k, int3
 template <class LaunchRound>
 int run_rounds_once(LaunchRound& launch_round, const CandBuffers& b, int32_t cap, int32_t k, int32_t n_queries, int32_t n_active,
                     const int32_t* q_list, int32_t n_units, int32_t round0_units, bool safe, int64_t doc_id_base,
-                    float* out_scores, int64_t* out_ids, int32_t* out_counts, cudaStream_t stream) {
-    int unit = 0, size = round0_units;
+                    float* out_scores, int64_t* out_ids, int32_t* out_counts, cudaStream_t stream,
+                    const b200ret_round_exchange* ex = nullptr) {
+    int unit = 0, size = round0_units, exchanged = 0;
+    auto exchange = [&]() -> int {     // all shards: MIN of the published bounds, then raise tau (see b200ret.h (3b))
+        if (ex->hook(ex->user) != 0) {
+            set_err("search: the tau-exchange hook failed");
+            return B200RET_EINVAL;
+        }
+        ++exchanged;
+        return launch_tau_raise(b.tau, ex->aux, n_queries, stream);
+    };
+    if (ex) {
+        int rc = launch_aux_init(ex->aux, n_queries, stream);
+        if (rc != B200RET_OK) return rc;
+    }
     while (unit < n_units) {
         const int end = (n_units - unit <= size) ? n_units : unit + size;
         int rc = launch_round(unit, end, q_list, n_active);
         if (rc != B200RET_OK) return rc;
         if (end < n_units) {
-            rc = launch_select(false, b, cap, k, n_queries, n_active, q_list, doc_id_base, nullptr, nullptr, nullptr, stream);
+            const bool ex_now = ex && exchanged < ex->n_exchanges;
+            rc = launch_select(false, b, cap, k, n_queries, n_active, q_list, doc_id_base, nullptr, nullptr, nullptr, stream,
+                               ex_now ? ex->aux_rank : 0, ex_now ? ex->aux : nullptr);
             if (rc != B200RET_OK) return rc;
+            if (ex_now && (rc = exchange()) != B200RET_OK) return rc;
         }
         unit = end;
         // geometric schedule: the next round covers (ROUND_GROWTH - 1) x the docs seen so far, so about
         // (ROUND_GROWTH - 1) * k new candidates per query survive tau on exchangeable data (capacity: see the header)
         if (!safe) size = unit * (ROUND_GROWTH - 1);
+    }
+    // a shard smaller than the largest one has fewer rounds: it still takes part in the remaining exchanges (collectives)
+    while (ex && exchanged < ex->n_exchanges) {
+        const int rc = exchange();
+        if (rc != B200RET_OK) return rc;
     }
     return launch_select(true, b, cap, k, n_queries, n_active, q_list, doc_id_base, out_scores, out_ids, out_counts, stream);
 }
@@ -81,11 +117,15 @@ int run_rounds_once(LaunchRound& launch_round, const CandBuffers& b, int32_t cap
 template <class LaunchRound>
 int run_search(LaunchRound& launch_round, const CandBuffers& b, int32_t cap, int32_t k, int32_t n_queries, int32_t n_units,
                int32_t round0_units, float threshold, int64_t doc_id_base, float* out_scores, int64_t* out_ids,
-               int32_t* out_counts, cudaStream_t stream) {
+               int32_t* out_counts, cudaStream_t stream, const b200ret_round_exchange* ex = nullptr) {
+    if (ex && (ex->aux_rank < 1 || ex->n_exchanges < 0 || !ex->aux || !ex->hook)) {
+        set_err("search: bad round exchange (aux_rank %d, n_exchanges %d)", ex->aux_rank, ex->n_exchanges);
+        return B200RET_EINVAL;
+    }
     int rc = launch_cand_init(b, n_queries, threshold, stream);
     if (rc != B200RET_OK) return rc;
     rc = run_rounds_once(launch_round, b, cap, k, n_queries, n_queries, nullptr, n_units, round0_units, /*safe=*/false,
-                             doc_id_base, out_scores, out_ids, out_counts, stream);
+                             doc_id_base, out_scores, out_ids, out_counts, stream, ex);
     if (rc != B200RET_OK) return rc;
 
     // The only host round trip: did any candidate list overflow?

@@ -399,9 +399,9 @@ extern "C" size_t b200ret_dense_search_workspace_bytes(int32_t n_queries, int32_
     return carve_cand(ws, n_queries, dense_cap(k), nullptr) + 256;
 }
 
-extern "C" int b200ret_dense_search(const void* corpus_bf16, const void* queries_bf16, int32_t n_docs, int32_t n_queries, int32_t dim,
-                                    int32_t k, int64_t doc_id_base, float* out_scores, int64_t* out_ids, int32_t* out_counts,
-                                    void* workspace, size_t workspace_bytes, void* stream_) {
+static int dense_search_impl(const void* corpus_bf16, const void* queries_bf16, int32_t n_docs, int32_t n_queries, int32_t dim,
+                             int32_t k, int64_t doc_id_base, float* out_scores, int64_t* out_ids, int32_t* out_counts,
+                             void* workspace, size_t workspace_bytes, void* stream_, const b200ret_round_exchange* exchange) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     B200RET_REQUIRE(k >= 1 && k <= B200RET_MAX_K, "dense_search: k=%d outside [1, %d]", k, B200RET_MAX_K);
     B200RET_REQUIRE(n_queries >= 0 && n_docs >= 0, "dense_search: bad sizes");
@@ -473,5 +473,24 @@ extern "C" int b200ret_dense_search(const void* corpus_bf16, const void* queries
         return B200RET_OK;
     };
     return run_search(launch_round, b, cap, k, n_queries, n_units, D_ROUND0_DOCS / D_UNIT_DOCS, -INFINITY, doc_id_base, out_scores,
-                      out_ids, out_counts, stream);
+                      out_ids, out_counts, stream, exchange);
+}
+
+extern "C" int b200ret_dense_search(const void* corpus_bf16, const void* queries_bf16, int32_t n_docs, int32_t n_queries, int32_t dim,
+                                    int32_t k, int64_t doc_id_base, float* out_scores, int64_t* out_ids, int32_t* out_counts,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+    return dense_search_impl(corpus_bf16, queries_bf16, n_docs, n_queries, dim, k, doc_id_base, out_scores, out_ids, out_counts,
+                             workspace, workspace_bytes, stream, nullptr);
+}
+
+extern "C" int32_t b200ret_dense_exchange_rounds(int32_t n_docs_largest_shard) {
+    return schedule_exchanges((max(n_docs_largest_shard, 0) + D_UNIT_DOCS - 1) / D_UNIT_DOCS, D_ROUND0_DOCS / D_UNIT_DOCS);
+}
+
+extern "C" int b200ret_dense_search_sharded(const void* corpus_bf16, const void* queries_bf16, int32_t n_docs, int32_t n_queries,
+                                            int32_t dim, int32_t k, int64_t doc_id_base, float* out_scores, int64_t* out_ids,
+                                            int32_t* out_counts, void* workspace, size_t workspace_bytes, void* stream,
+                                            const b200ret_round_exchange* exchange) {
+    return dense_search_impl(corpus_bf16, queries_bf16, n_docs, n_queries, dim, k, doc_id_base, out_scores, out_ids, out_counts,
+                             workspace, workspace_bytes, stream, exchange);
 }

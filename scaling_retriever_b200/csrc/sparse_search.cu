@@ -796,7 +796,7 @@ static int sparse_search_impl(int format, const uint32_t* table, const void* pos
                               const int32_t* q_offsets, const int32_t* q_terms, const float* q_weights,
                               int32_t n_queries, int32_t k, float threshold, int64_t doc_id_base,
                               float* out_scores, int64_t* out_ids, int32_t* out_counts,
-                              void* workspace, size_t workspace_bytes, void* stream_) {
+                              void* workspace, size_t workspace_bytes, void* stream_, const b200ret_round_exchange* exchange = nullptr) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     ScoreParams sp;
     int rc = fill_params(sp, table, postings, n_docs, block_docs, q_offsets, q_terms, q_weights, n_queries);
@@ -830,7 +830,7 @@ static int sparse_search_impl(int format, const uint32_t* table, const void* pos
         return launch_score(r, stream);
     };
     return run_search(launch_round, b, cap, k, n_queries, n_blocks, ROUND0_BLOCKS, threshold, doc_id_base, out_scores, out_ids,
-                      out_counts, stream);
+                      out_counts, stream, exchange);
 }
 
 extern "C" int b200ret_sparse_search(const uint32_t* table, const void* postings, int32_t n_terms, int32_t n_docs, int32_t block_docs,
@@ -847,4 +847,18 @@ extern "C" int b200ret_sparse_search_f16(const uint32_t* table, const void* post
                                          int64_t* out_ids, int32_t* out_counts, void* workspace, size_t workspace_bytes, void* stream) {
     return sparse_search_impl(1, table, postings, n_terms, n_docs, block_docs, q_offsets, q_terms, q_weights, n_queries, k, threshold,
                               doc_id_base, out_scores, out_ids, out_counts, workspace, workspace_bytes, stream);
+}
+
+extern "C" int32_t b200ret_sparse_exchange_rounds(int32_t n_docs_largest_shard) {
+    const int bd = block_docs_of_shape();
+    return schedule_exchanges((std::max(n_docs_largest_shard, 0) + bd - 1) / bd, ROUND0_BLOCKS);
+}
+
+extern "C" int b200ret_sparse_search_sharded(const uint32_t* table, const void* postings, int32_t n_terms, int32_t n_docs,
+                                             int32_t block_docs, const int32_t* q_offsets, const int32_t* q_terms,
+                                             const float* q_weights, int32_t n_queries, int32_t k, float threshold, int64_t doc_id_base,
+                                             float* out_scores, int64_t* out_ids, int32_t* out_counts, void* workspace,
+                                             size_t workspace_bytes, void* stream, const b200ret_round_exchange* exchange) {
+    return sparse_search_impl(0, table, postings, n_terms, n_docs, block_docs, q_offsets, q_terms, q_weights, n_queries, k, threshold,
+                              doc_id_base, out_scores, out_ids, out_counts, workspace, workspace_bytes, stream, exchange);
 }

@@ -369,7 +369,12 @@ class DenseFlatIndexer(DenseIndexer):
         with torch.cuda.device(self.device):
             q = _stage_in(self._staging, self.device, "queries", query_reps, torch.float32)   # pinned -> device
             q16 = ops.f32_to_bf16(q)
-            scores, ids, _ = ops.dense_search(self.index, q16, int(top_docs), doc_id_base=self._row_lo)
+            exchange = None
+            if _world_size() > 1:     # the shards exchange their bounds between the rounds (shard.TauExchange)
+                if self._staging.get("tau_exchange") is None:
+                    self._staging["tau_exchange"] = shard.TauExchange("dense", self._n_total, self.device)
+                exchange = self._staging["tau_exchange"]
+            scores, ids, _ = ops.dense_search(self.index, q16, int(top_docs), doc_id_base=self._row_lo, exchange=exchange)
             if _world_size() > 1:
                 if host_ranks == "first" and self._n_total < shard.KEY_ID_LIMIT:
                     key = (scores.shape[0], int(top_docs))
@@ -637,7 +642,14 @@ class SparseRetrieval:
             return tuple(o.numpy() for o in out)
 
     def _search_local(self, d_off, d_terms, d_w, topk, threshold):
-        """This rank's rows: one kernel pass per local doc-range index, merged when there are several."""
+        """This rank's rows: one kernel pass per local doc-range index, merged when there are several.  Sharded over ranks
+        (one fp32 index per rank): the shards exchange their bounds between the rounds (shard.TauExchange)."""
+        if self.shard_plan.world_size > 1 and len(self.device_shards) == 1 and self.device_shards[0][0].weight_format == "fp32":
+            if self._staging.get("tau_exchange") is None:
+                self._staging["tau_exchange"] = shard.TauExchange("sparse", self.size_collection, self._cuda)
+            index, base = self.device_shards[0]
+            return ops.sparse_search(index, d_off, d_terms, d_w, topk, threshold, doc_id_base=base,
+                                     exchange=self._staging["tau_exchange"])
         parts = [ops.sparse_search(index, d_off, d_terms, d_w, topk, threshold, doc_id_base=base) for index, base in self.device_shards]
         if len(parts) == 1:
             return parts[0]

@@ -165,10 +165,11 @@ class SparseDeviceIndex:
         return cls.from_csr(term_offsets, doc_ids, weights, n_docs, weight_format=weight_format)
 
 
-def sparse_search(index, q_offsets, q_terms, q_weights, k, threshold=0.0, doc_id_base=0):
+def sparse_search(index, q_offsets, q_terms, q_weights, k, threshold=0.0, doc_id_base=0, exchange=None):
     """Score a CSR-packed query batch against `index`; return (scores fp32[Q,k], ids int64[Q,k], counts int32[Q]).
 
-    Rows are sorted by (score desc, doc id asc); slots past counts[q] hold (-inf, -1).
+    Rows are sorted by (score desc, doc id asc); slots past counts[q] hold (-inf, -1).  `exchange` (shard.TauExchange): this
+    index is one doc-range shard of a sharded search whose shards exchange their bounds between the rounds.
     """
     lib = _lib.load()
     _check_cuda("q_offsets", q_offsets, torch.int32)
@@ -182,11 +183,16 @@ def sparse_search(index, q_offsets, q_terms, q_weights, k, threshold=0.0, doc_id
         out_counts = torch.empty(n_queries, dtype=torch.int32, device=dev)
         ws_bytes = lib.b200ret_sparse_search_workspace_bytes(n_queries, k)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        entry = lib.b200ret_sparse_search_f16 if index.weight_format == "fp16" else lib.b200ret_sparse_search
-        _lib.check(entry(
-            _ptr(index.table), _ptr(index.postings), index.n_terms, index.n_docs, index.block_docs,
-            _ptr(q_offsets), _ptr(q_terms), _ptr(q_weights), n_queries, k, float(threshold), int(doc_id_base),
-            _ptr(out_scores), _ptr(out_ids), _ptr(out_counts), _ptr(ws), ws_bytes, _stream()))
+        args = (_ptr(index.table), _ptr(index.postings), index.n_terms, index.n_docs, index.block_docs,
+                _ptr(q_offsets), _ptr(q_terms), _ptr(q_weights), n_queries, k, float(threshold), int(doc_id_base),
+                _ptr(out_scores), _ptr(out_ids), _ptr(out_counts), _ptr(ws), ws_bytes, _stream())
+        if exchange is not None:
+            if index.weight_format != "fp32":
+                raise ValueError("the tau exchange of a sharded search is implemented for the fp32 posting format only")
+            _lib.check(lib.b200ret_sparse_search_sharded(*args, exchange.struct(n_queries, k)))
+        else:
+            entry = lib.b200ret_sparse_search_f16 if index.weight_format == "fp16" else lib.b200ret_sparse_search
+            _lib.check(entry(*args))
     return out_scores, out_ids, out_counts
 
 
@@ -218,8 +224,8 @@ def f32_to_bf16(src):
     return dst
 
 
-def dense_search(corpus, queries, k, doc_id_base=0):
-    """Exact top-k of queries . corpus^T (bf16 inputs, fp32 accumulate); rows sorted descending."""
+def dense_search(corpus, queries, k, doc_id_base=0, exchange=None):
+    """Exact top-k of queries . corpus^T (bf16 inputs, fp32 accumulate); rows sorted descending.  `exchange`: see sparse_search."""
     lib = _lib.load()
     _check_cuda("corpus", corpus, torch.bfloat16)
     _check_cuda("queries", queries, torch.bfloat16)
@@ -234,8 +240,12 @@ def dense_search(corpus, queries, k, doc_id_base=0):
         out_counts = torch.empty(n_queries, dtype=torch.int32, device=dev)
         ws_bytes = lib.b200ret_dense_search_workspace_bytes(n_queries, n_docs, dim, k)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        _lib.check(lib.b200ret_dense_search(_ptr(corpus), _ptr(queries), n_docs, n_queries, dim, k, int(doc_id_base),
-                                            _ptr(out_scores), _ptr(out_ids), _ptr(out_counts), _ptr(ws), ws_bytes, _stream()))
+        args = (_ptr(corpus), _ptr(queries), n_docs, n_queries, dim, k, int(doc_id_base),
+                _ptr(out_scores), _ptr(out_ids), _ptr(out_counts), _ptr(ws), ws_bytes, _stream())
+        if exchange is not None:
+            _lib.check(lib.b200ret_dense_search_sharded(*args, exchange.struct(n_queries, k)))
+        else:
+            _lib.check(lib.b200ret_dense_search(*args))
     return out_scores, out_ids, out_counts
 
 

@@ -46,6 +46,28 @@ def main():
     s, i, c = shard.merge_shards(loc_s, loc_i, k, n_docs_total=1 << 33)      # ids beyond a key's 32 bits take that exchange
     assert torch.equal(i, ref_i), "sparse 64-bit fallback"
 
+    # ---- sparse: tau exchange between the rounds (shard.TauExchange), shards with DIFFERENT round counts --------------------
+    bd = ops.block_docs()
+    n2 = world * 8 * bd + 1          # ranks 0..G-2: 8 blocks + 1 doc (9 blocks, 3 rounds); last rank: 8 blocks (2 rounds + 1 extra exchange)
+    rows2, cols2, vals2 = synth.gen_sparse_docs(n2, n_terms=n_terms, mean_nnz=20, seed=15, device=dev)
+    full2 = ops.SparseDeviceIndex.from_coo(rows2, cols2, vals2, n_terms, n2)
+    for kk, thr in ((100, 0.0), (1000, 0.0), (37, 1.5)):
+        r_s, r_i, r_c = ops.sparse_search(full2, q_off, q_t, q_w, kk, thr)
+        lo2, hi2 = shard.ShardPlan(n2, world).bounds(rank)
+        keep2 = (rows2 >= lo2) & (rows2 < hi2)
+        part2 = ops.SparseDeviceIndex.from_coo((rows2[keep2] - lo2).contiguous(), cols2[keep2].contiguous(), vals2[keep2].contiguous(),
+                                               n_terms, hi2 - lo2)
+        ex = shard.TauExchange("sparse", n2, dev)
+        assert ex.n_exchanges == 2, ex.n_exchanges
+        for _ in range(2):           # the exchange object is reused across searches
+            s, i, c = ops.sparse_search(part2, q_off, q_t, q_w, kk, thr, doc_id_base=lo2, exchange=ex)
+            plain = ops.sparse_search(part2, q_off, q_t, q_w, kk, thr, doc_id_base=lo2)
+            # with the exchanged bound a shard keeps only what can still reach the global top-k: a subset of its plain local rows
+            assert bool((c <= plain[2]).all())
+            s, i, c = shard.merge_shards(s, i, kk, n_docs_total=n2)
+            assert torch.equal(i, r_i) and torch.equal(c, r_c) and torch.equal(s.view(torch.int32), r_s.view(torch.int32)), ("tau exchange", kk)
+    del full2, part2, rows2, cols2, vals2
+
     # ---- sparse: class API (SparseRetrieval shards by itself under a process group) ------------------------------------
     index = IndexDictOfArray(index_path=None, dim_voc=n_terms, device=dev)
     index.add_batch_document(rows, cols, vals, n_docs=n_docs)
@@ -77,6 +99,18 @@ def main():
     s, i, _ = ops.dense_search(docs[lo:hi].contiguous(), q16, kd, doc_id_base=lo)
     s, i, _ = shard.merge_shards(s, i, kd, n_docs_total=nd)
     assert torch.equal(i, ref_i) and torch.equal(s.view(torch.int32), ref_s.view(torch.int32)), "dense ops"
+    # dense tau exchange, shards with different round counts (129 vs 128 tiles of 256 docs)
+    nd2 = world * 32768 + 1
+    docs2 = synth.gen_dense(nd2, dim, seed=17, device=dev, dtype=torch.bfloat16)
+    r_s, r_i, _ = ops.dense_search(docs2, q16, kd)
+    lo2, hi2 = shard.ShardPlan(nd2, world).bounds(rank)
+    ex = shard.TauExchange("dense", nd2, dev)
+    assert ex.n_exchanges == 2, ex.n_exchanges
+    s, i, _ = ops.dense_search(docs2[lo2:hi2].contiguous(), q16, kd, doc_id_base=lo2, exchange=ex)
+    s, i, _ = shard.merge_shards(s, i, kd, n_docs_total=nd2)
+    assert torch.equal(i, r_i) and torch.equal(s.view(torch.int32), r_s.view(torch.int32)), "dense tau exchange"
+    del docs2
+
     flat = DenseFlatIndexer(device=dev)
     flat.init_index(dim)
     flat.index_data(docs.float().cpu().numpy(), [f"P{j}" for j in range(nd)])
