@@ -105,13 +105,17 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(uint64_t* cand, 
     __syncthreads();
 #endif
     int kept = c;
-    if (want_aux && c >= aux_rank) {        // block-uniform; the keys in shared memory are only read by the selections
-        const uint64_t mth = block_radix_select_kth(skeys, c, aux_rank, hist, bcast);
-        if (threadIdx.x == 0) aux[q] = cand_score(mth);
-        __syncthreads();
+    // tau exchange: a score that at least aux_rank of this shard's candidates reach — read off the first histogram of the
+    // selection below (no extra pass over the keys); when nothing has to be cut the same call only serves that purpose
+    __shared__ uint64_t aux_lower;
+    const bool publish = want_aux && c >= aux_rank;     // block-uniform
+    if (publish && c <= k) {
+        block_radix_select_kth(skeys, c, 1, hist, bcast, aux_rank, &aux_lower, /*first_pass_only=*/true);
+        if (threadIdx.x == 0) aux[q] = cand_score(aux_lower);
     }
     if (c > k) {
-        const uint64_t kth = block_radix_select_kth(skeys, c, k, hist, bcast);
+        const uint64_t kth = block_radix_select_kth(skeys, c, k, hist, bcast, publish ? aux_rank : 0, &aux_lower);
+        if (publish && threadIdx.x == 0) aux[q] = cand_score(aux_lower);
         // Compact the k winners to the front of the global list (their order there is irrelevant).
         for (int i = threadIdx.x; i < c; i += blockDim.x) {
             const uint64_t key = skeys[i];

@@ -21,8 +21,12 @@ namespace b200ret {
 //   0.2-0.3 ms each, a per-rank fixed cost that does not shrink with the shard).
 // * Early exit: as soon as the bucket that holds the k-th key contains exactly as many keys as are still needed, every key of
 //   that bucket is selected and the k-th key is simply the bucket's minimum (one min pass instead of the remaining passes).
+// Optional by-product (`m` > 0, `m_lower` a shared-memory slot): a key that at least `m` of the keys reach (1 <= m <= n) —
+// the lower edge of the FIRST histogram's bucket that holds the m-th largest key.  It costs one more walk over the 256
+// counters; the tau exchange of a sharded search publishes its score (candidates.cu).
 __device__ inline uint64_t block_radix_select_kth(const uint64_t* keys, int n, int k, uint32_t* hist,
-                                                  uint64_t* bcast) {
+                                                  uint64_t* bcast, int m = 0, uint64_t* m_lower = nullptr,
+                                                  bool first_pass_only = false) {
     // ---- highest differing bit ----
     if (threadIdx.x == 0) bcast[0] = 0;
     __syncthreads();
@@ -37,12 +41,16 @@ __device__ inline uint64_t block_radix_select_kth(const uint64_t* keys, int n, i
     __syncthreads();
     const uint64_t diff = bcast[0];
     __syncthreads();
-    if (diff == 0) return keys[0];                                      // all keys equal (n == 1, keys are unique otherwise)
+    if (diff == 0) {                                                    // all keys equal (n == 1, keys are unique otherwise)
+        if (m > 0 && threadIdx.x == 0) *m_lower = keys[0];
+        __syncthreads();
+        return keys[0];
+    }
     int hi = 63 - __clzll(static_cast<long long>(diff));                // block-uniform
     uint64_t mask = (hi == 63) ? 0ull : ~((2ull << hi) - 1ull);         // bits above the first differing one: common to all keys
     uint64_t prefix = keys[0] & mask;
     int remaining = k;
-    bool first = true;
+    bool first = true, first_pass = true;
     while (hi >= 0) {
         const int lo = max(0, hi - 7);
         const uint32_t dmask = (1u << (hi - lo + 1)) - 1u;
@@ -99,7 +107,37 @@ __device__ inline uint64_t block_radix_select_kth(const uint64_t* keys, int n, i
                 }
             }
         }
+        if (first_pass && m > 0 && threadIdx.x >= 32 && threadIdx.x < 64) {
+            // warp 1: the bucket of the m-th largest key in this (first) histogram -> its lower edge
+            const int l = threadIdx.x - 32;
+            uint32_t c[8];
+            uint32_t local = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                c[j] = hist[255 - (l * 8 + j)];
+                local += c[j];
+            }
+            uint32_t incl = local;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+                if (l >= off) incl += v;
+            }
+            uint32_t above = incl - local;
+            if (above < static_cast<uint32_t>(m) && incl >= static_cast<uint32_t>(m)) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (above + c[j] >= static_cast<uint32_t>(m)) {
+                        *m_lower = prefix | (static_cast<uint64_t>(255 - (l * 8 + j)) << lo);
+                        break;
+                    }
+                    above += c[j];
+                }
+            }
+        }
         __syncthreads();
+        if (first_pass && first_pass_only) return 0;     // the caller only wanted the by-product (block-uniform)
+        first_pass = false;
         const uint64_t digit = bcast[0];
         remaining = static_cast<int>(bcast[1]);
         prefix |= digit << lo;
