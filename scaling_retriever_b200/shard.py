@@ -125,7 +125,7 @@ class TauExchange:
 
     Alone, a shard can only raise its eligibility bound tau[q] to ITS k-th best score, so every shard emits and selects as many
     candidates per round as a whole corpus would — the per-round cost that kept 8 GPUs at 0.85 of linear.  With the exchange
-    each shard publishes, after every round, the score of its ceil(k/G)-th best candidate; one MIN all-reduce of that [Q]
+    each shard publishes, after every round, a score that at least ceil(k/G) of its candidates reach; one MIN all-reduce of that [Q]
     vector (28 KB, NCCL over NVLink, enqueued on the search's stream by the hook below — no host synchronisation) gives a
     bound that at least k documents of the whole corpus reach, and every shard continues with it.  The result is unchanged
     (exactly the global top-k after the merge); candidates per shard and round drop from ~3 k to ~3 k / G.

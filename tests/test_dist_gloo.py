@@ -81,6 +81,17 @@ def _worker(rank, world, port, tmp):
     ok = ok and np.array_equal(u_ids, full[1]) and np.array_equal(u_scores.view(np.uint32), full[0].view(np.uint32)) \
         and np.array_equal(u_counts, full[2])
 
+    # tau exchange (shard.TauExchange): the hook the C library calls between rounds is one MIN all-reduce of the published bounds;
+    # every rank takes part in the same number of exchanges (the schedule of the LARGEST shard)
+    ex = shard.TauExchange("sparse", n_docs, torch.device("cpu"))
+    ex.struct(nq, k)
+    from scaling_retriever_b200 import _lib
+    lib = _lib.load()
+    ok = ok and ex.n_exchanges == lib.b200ret_sparse_exchange_rounds(shard.ShardPlan(n_docs, world).per_shard)
+    ok = ok and ex._struct.aux_rank == (k + world - 1) // world and ex._struct.n_exchanges == ex.n_exchanges
+    ex.aux.copy_(torch.arange(nq, dtype=torch.float32) + 10.0 * rank)
+    ok = ok and ex._on_round(None) == 0 and bool(torch.equal(ex.aux, torch.arange(nq, dtype=torch.float32)))
+
     # shared host rows (shard.SharedHostRows): every rank writes its merged query slice, the first worker reads all of them
     host = shard.SharedHostRows(nq, k)
     a, b = rank * qs, min(nq, (rank + 1) * qs)
@@ -132,3 +143,25 @@ def test_merge_reference_total_order():
     i = np.array([[[5, 9, -1]], [[4, 7, 6]]], dtype=np.int64)
     out_s, out_i, c = merge_rows_reference(s, i, 4)
     assert out_i.tolist() == [[4, 5, 6, 7]] and out_s.tolist() == [[3., 3., 2., 2.]] and c.tolist() == [4]
+
+
+def test_exchange_round_counts_follow_the_geometric_schedule():
+    """b200ret_*_exchange_rounds = select launches between the rounds of candidates.cuh's schedule (first round r0 units, then the
+    docs seen grow 4x per round) — what every shard must agree on before a sharded search."""
+    sys.path.insert(0, ROOT)
+    from scaling_retriever_b200 import _lib, ops
+    lib = _lib.load()
+    bd = ops.block_docs()
+
+    def rounds(n_units, r0, growth=4):
+        unit, size, selects = 0, r0, 0
+        while unit < n_units:
+            end = n_units if n_units - unit <= size else unit + size
+            selects += end < n_units
+            unit, size = end, end * (growth - 1)
+        return selects
+    for blocks in (0, 1, 2, 3, 8, 9, 32, 33, 309, 2468):
+        assert lib.b200ret_sparse_exchange_rounds(blocks * bd) == rounds(blocks, 2), blocks
+    assert lib.b200ret_sparse_exchange_rounds(8 * bd + 1) == rounds(9, 2) == 2
+    for tiles in (0, 1, 32, 33, 128, 129, 4317):
+        assert lib.b200ret_dense_exchange_rounds(tiles * 256) == rounds(tiles, 32), tiles
