@@ -644,7 +644,13 @@ class SparseRetrieval:
     def _search_local(self, d_off, d_terms, d_w, topk, threshold):
         """This rank's rows: one kernel pass per local doc-range index, merged when there are several.  Sharded over ranks
         (one fp32 index per rank): the shards exchange their bounds between the rounds (shard.TauExchange)."""
-        if self.shard_plan.world_size > 1 and len(self.device_shards) == 1 and self.device_shards[0][0].weight_format == "fp32":
+        if self.shard_plan.world_size > 1 and self._staging.get("exchange_ok") is None:
+            # the exchange is a collective inside the search: every rank must take the same decision (first search only)
+            mine = len(self.device_shards) == 1 and self.device_shards[0][0].weight_format == "fp32"
+            flag = torch.tensor([int(mine)], dtype=torch.int32, device=self._cuda)
+            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+            self._staging["exchange_ok"] = bool(flag.item())
+        if self.shard_plan.world_size > 1 and self._staging["exchange_ok"]:
             if self._staging.get("tau_exchange") is None:
                 self._staging["tau_exchange"] = shard.TauExchange("sparse", self.size_collection, self._cuda)
             index, base = self.device_shards[0]
