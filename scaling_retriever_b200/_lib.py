@@ -21,8 +21,8 @@ _c_int = ctypes.c_int
 class RoundExchange(ctypes.Structure):
     """b200ret_round_exchange (include/b200ret.h (3b)): the tau exchange between the rounds of a sharded search."""
     HOOK = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p)
-    _fields_ = [("aux_rank", ctypes.c_int32), ("n_exchanges", ctypes.c_int32), ("aux", ctypes.c_void_p),
-                ("hook", HOOK), ("user", ctypes.c_void_p)]
+    _fields_ = [("aux_rank", ctypes.c_int32), ("n_exchanges", ctypes.c_int32), ("growth", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("aux", ctypes.c_void_p), ("hook", HOOK), ("user", ctypes.c_void_p)]
 
 
 # name -> (restype, argtypes); kept in one table so tests can check the exported symbol set.
@@ -51,8 +51,9 @@ PROTOTYPES = {
                                            _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_sz, _c_ptr]),
     "b200ret_sparse_scores_f16": (_c_int, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32,
                                            _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_ptr, _c_ptr, _c_sz, _c_ptr]),
-    "b200ret_sparse_exchange_rounds": (_c_i32, [_c_i32]),
-    "b200ret_dense_exchange_rounds": (_c_i32, [_c_i32]),
+    "b200ret_exchange_growth": (_c_i32, [_c_i32]),
+    "b200ret_sparse_exchange_rounds": (_c_i32, [_c_i32, _c_i32]),
+    "b200ret_dense_exchange_rounds": (_c_i32, [_c_i32, _c_i32]),
     "b200ret_sparse_search_sharded": (_c_int, [_c_ptr, _c_ptr, _c_i32, _c_i32, _c_i32,
                                                _c_ptr, _c_ptr, _c_ptr, _c_i32, _c_i32, _c_f32, _c_i64,
                                                _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_sz, _c_ptr, ctypes.POINTER(RoundExchange)]),

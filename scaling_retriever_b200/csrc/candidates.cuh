@@ -10,6 +10,8 @@
 // of head-room over that expectation for every k up to B200RET_MAX_K.  A list that overflows anyway (adversarial doc
 // order) is flagged and the query is re-run with fixed rounds of the first-round size, which cannot overflow.
 #pragma once
+#include <algorithm>
+
 #include "common.cuh"
 #include "topk_select.cuh"
 
@@ -46,16 +48,18 @@ inline size_t carve_cand(Workspace& ws, int32_t n_queries, int32_t cap, CandBuff
 }
 
 // Non-final round count of the geometric schedule (= select launches between rounds) for `n_units` units.
-inline int32_t schedule_exchanges(int32_t n_units, int32_t round0_units) {
-    int32_t unit = 0, size = round0_units, selects = 0;
+inline int32_t schedule_exchanges(int32_t n_units, int32_t round0_units, int32_t growth) {
+    int64_t unit = 0, size = round0_units;
+    int32_t selects = 0;
     while (unit < n_units) {
-        const int32_t end = (n_units - unit <= size) ? n_units : unit + size;
+        const int64_t end = (n_units - unit <= size) ? n_units : unit + size;
         if (end < n_units) ++selects;
         unit = end;
-        size = unit * (ROUND_GROWTH - 1);
+        size = unit * (growth - 1);
     }
     return selects;
 }
+inline int32_t exchange_growth(int32_t n_shards) { return n_shards > 1 ? 2 * n_shards + 1 : ROUND_GROWTH; }
 
 // Kernels + launchers live in candidates.cu (one definition for both searches).
 int launch_cand_init(const CandBuffers& b, int32_t n_queries, float threshold, cudaStream_t stream);
@@ -78,6 +82,7 @@ int run_rounds_once(LaunchRound& launch_round, const CandBuffers& b, int32_t cap
                     float* out_scores, int64_t* out_ids, int32_t* out_counts, cudaStream_t stream,
                     const b200ret_round_exchange* ex = nullptr) {
     int unit = 0, size = round0_units, exchanged = 0;
+    const int growth = (ex && !safe) ? ex->growth : ROUND_GROWTH;    // a sharded search with the exchange takes larger steps
     auto exchange = [&]() -> int {     // all shards: MIN of the published bounds, then raise tau (see b200ret.h (3b))
         if (ex->hook(ex->user) != 0) {
             set_err("search: the tau-exchange hook failed");
@@ -104,7 +109,7 @@ int run_rounds_once(LaunchRound& launch_round, const CandBuffers& b, int32_t cap
         unit = end;
         // geometric schedule: the next round covers (ROUND_GROWTH - 1) x the docs seen so far, so about
         // (ROUND_GROWTH - 1) * k new candidates per query survive tau on exchangeable data (capacity: see the header)
-        if (!safe) size = unit * (ROUND_GROWTH - 1);
+        if (!safe) size = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(unit) * (growth - 1), n_units));
     }
     // a shard smaller than the largest one has fewer rounds: it still takes part in the remaining exchanges (collectives)
     while (ex && exchanged < ex->n_exchanges) {
@@ -118,8 +123,8 @@ template <class LaunchRound>
 int run_search(LaunchRound& launch_round, const CandBuffers& b, int32_t cap, int32_t k, int32_t n_queries, int32_t n_units,
                int32_t round0_units, float threshold, int64_t doc_id_base, float* out_scores, int64_t* out_ids,
                int32_t* out_counts, cudaStream_t stream, const b200ret_round_exchange* ex = nullptr) {
-    if (ex && (ex->aux_rank < 1 || ex->n_exchanges < 0 || !ex->aux || !ex->hook)) {
-        set_err("search: bad round exchange (aux_rank %d, n_exchanges %d)", ex->aux_rank, ex->n_exchanges);
+    if (ex && (ex->aux_rank < 1 || ex->n_exchanges < 0 || ex->growth < 2 || !ex->aux || !ex->hook)) {
+        set_err("search: bad round exchange (aux_rank %d, n_exchanges %d, growth %d)", ex->aux_rank, ex->n_exchanges, ex->growth);
         return B200RET_EINVAL;
     }
     int rc = launch_cand_init(b, n_queries, threshold, stream);

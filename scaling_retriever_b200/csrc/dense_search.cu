@@ -483,8 +483,9 @@ extern "C" int b200ret_dense_search(const void* corpus_bf16, const void* queries
                              workspace, workspace_bytes, stream, nullptr);
 }
 
-extern "C" int32_t b200ret_dense_exchange_rounds(int32_t n_docs_largest_shard) {
-    return schedule_exchanges((max(n_docs_largest_shard, 0) + D_UNIT_DOCS - 1) / D_UNIT_DOCS, D_ROUND0_DOCS / D_UNIT_DOCS);
+extern "C" int32_t b200ret_dense_exchange_rounds(int32_t n_docs_largest_shard, int32_t n_shards) {
+    return schedule_exchanges((max(n_docs_largest_shard, 0) + D_UNIT_DOCS - 1) / D_UNIT_DOCS, D_ROUND0_DOCS / D_UNIT_DOCS,
+                              exchange_growth(n_shards));
 }
 
 extern "C" int b200ret_dense_search_sharded(const void* corpus_bf16, const void* queries_bf16, int32_t n_docs, int32_t n_queries,

@@ -849,9 +849,11 @@ extern "C" int b200ret_sparse_search_f16(const uint32_t* table, const void* post
                               doc_id_base, out_scores, out_ids, out_counts, workspace, workspace_bytes, stream);
 }
 
-extern "C" int32_t b200ret_sparse_exchange_rounds(int32_t n_docs_largest_shard) {
+extern "C" int32_t b200ret_exchange_growth(int32_t n_shards) { return exchange_growth(n_shards); }
+
+extern "C" int32_t b200ret_sparse_exchange_rounds(int32_t n_docs_largest_shard, int32_t n_shards) {
     const int bd = block_docs_of_shape();
-    return schedule_exchanges((std::max(n_docs_largest_shard, 0) + bd - 1) / bd, ROUND0_BLOCKS);
+    return schedule_exchanges((std::max(n_docs_largest_shard, 0) + bd - 1) / bd, ROUND0_BLOCKS, exchange_growth(n_shards));
 }
 
 extern "C" int b200ret_sparse_search_sharded(const uint32_t* table, const void* postings, int32_t n_terms, int32_t n_docs,

@@ -47,8 +47,10 @@ def main():
     assert torch.equal(i, ref_i), "sparse 64-bit fallback"
 
     # ---- sparse: tau exchange between the rounds (shard.TauExchange), shards with DIFFERENT round counts --------------------
+    from scaling_retriever_b200 import _lib
+    growth = _lib.load().b200ret_exchange_growth(world)        # docs scored grow 2G + 1 times per round with the exchange
     bd = ops.block_docs()
-    n2 = world * 8 * bd + 1          # ranks 0..G-2: 8 blocks + 1 doc (9 blocks, 3 rounds); last rank: 8 blocks (2 rounds + 1 extra exchange)
+    n2 = world * 2 * growth * bd + 1  # ranks 0..G-2: 2g blocks + 1 doc (3 rounds); last rank: 2g blocks (2 rounds + 1 extra exchange)
     rows2, cols2, vals2 = synth.gen_sparse_docs(n2, n_terms=n_terms, mean_nnz=20, seed=15, device=dev)
     full2 = ops.SparseDeviceIndex.from_coo(rows2, cols2, vals2, n_terms, n2)
     for kk, thr in ((100, 0.0), (1000, 0.0), (37, 1.5)):
@@ -100,7 +102,7 @@ def main():
     s, i, _ = shard.merge_shards(s, i, kd, n_docs_total=nd)
     assert torch.equal(i, ref_i) and torch.equal(s.view(torch.int32), ref_s.view(torch.int32)), "dense ops"
     # dense tau exchange, shards with different round counts (129 vs 128 tiles of 256 docs)
-    nd2 = world * 32768 + 1
+    nd2 = world * 32 * growth * 256 + 1        # 32g + 1 tiles of 256 docs on ranks 0..G-2 (3 rounds), 32g on the last one (2 rounds)
     docs2 = synth.gen_dense(nd2, dim, seed=17, device=dev, dtype=torch.bfloat16)
     r_s, r_i, _ = ops.dense_search(docs2, q16, kd)
     lo2, hi2 = shard.ShardPlan(nd2, world).bounds(rank)
