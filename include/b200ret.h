@@ -205,9 +205,10 @@ typedef struct {
 } b200ret_round_exchange;
 
 /* Because the exchanged bound follows the documents ALL shards have seen, a shard may take larger steps without emitting more
- * candidates per round than an unsharded search does: the docs scored grow 2 * n_shards + 1 times per round instead of 4
- * times (about 2k * n_shards survivors per round over the whole corpus, 2k per shard, with head-room for the slack of
- * the bound).  Fewer rounds = fewer select launches, kernel tails and all-reduces per shard. */
+ * candidates per round than an unsharded search does: the docs scored grow max(4, n_shards + 1) times per round instead of
+ * 4 times (about k * n_shards survivors per round over the whole corpus, k per shard, which leaves head-room for the slack
+ * of the bound).  Fewer rounds = fewer select launches, kernel tails and all-reduces per shard.  A list that overflows anyway
+ * (shards that are not exchangeable) is re-run with the shard's own bounds and the plain schedule, then the safe one. */
 int32_t b200ret_exchange_growth(int32_t n_shards);
 int32_t b200ret_sparse_exchange_rounds(int32_t n_docs_largest_shard, int32_t n_shards);
 int32_t b200ret_dense_exchange_rounds(int32_t n_docs_largest_shard, int32_t n_shards);

@@ -11,6 +11,7 @@
 // order) is flagged and the query is re-run with fixed rounds of the first-round size, which cannot overflow.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "topk_select.cuh"
@@ -59,7 +60,10 @@ inline int32_t schedule_exchanges(int32_t n_units, int32_t round0_units, int32_t
     }
     return selects;
 }
-inline int32_t exchange_growth(int32_t n_shards) { return n_shards > 1 ? 2 * n_shards + 1 : ROUND_GROWTH; }
+inline int32_t exchange_growth(int32_t n_shards) {
+    if (const char* e = getenv("B200RET_TEST_EXCHANGE_GROWTH")) return std::max(2, atoi(e));     // test hook: force list overflows
+    return n_shards > 1 ? std::max(ROUND_GROWTH, n_shards + 1) : ROUND_GROWTH;
+}
 
 // Kernels + launchers live in candidates.cu (one definition for both searches).
 int launch_cand_init(const CandBuffers& b, int32_t n_queries, float threshold, cudaStream_t stream);
@@ -138,6 +142,23 @@ int run_search(LaunchRound& launch_round, const CandBuffers& b, int32_t cap, int
     B200RET_CUDA_CHECK(cudaMemcpyAsync(&any_overflow, b.overflow + n_queries, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     B200RET_CUDA_CHECK(cudaStreamSynchronize(stream));
     if (!any_overflow) return B200RET_OK;
+
+    if (ex) {
+        // A sharded search took larger steps on the strength of the exchanged bounds and a list overflowed (shards that are
+        // not exchangeable: the bound of the emptiest shard holds everybody back).  Middle tier: re-run those queries with
+        // this shard's own bounds and the plain geometric schedule (no collectives: the other shards are not involved).
+        rc = launch_cand_rearm(b, n_queries, threshold, stream);
+        if (rc != B200RET_OK) return rc;
+        int32_t n_mid = 0;
+        B200RET_CUDA_CHECK(cudaMemcpyAsync(&n_mid, b.n_list, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+        B200RET_CUDA_CHECK(cudaStreamSynchronize(stream));
+        rc = run_rounds_once(launch_round, b, cap, k, n_queries, n_mid, b.q_list, n_units, round0_units, /*safe=*/false, doc_id_base,
+                             out_scores, out_ids, out_counts, stream, nullptr);
+        if (rc != B200RET_OK) return rc;
+        B200RET_CUDA_CHECK(cudaMemcpyAsync(&any_overflow, b.overflow + n_queries, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+        B200RET_CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (!any_overflow) return B200RET_OK;
+    }
 
     rc = launch_cand_rearm(b, n_queries, threshold, stream);
     if (rc != B200RET_OK) return rc;

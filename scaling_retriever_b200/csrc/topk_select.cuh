@@ -107,33 +107,61 @@ __device__ inline uint64_t block_radix_select_kth(const uint64_t* keys, int n, i
                 }
             }
         }
-        if (first_pass && m > 0 && threadIdx.x >= 32 && threadIdx.x < 64) {
-            // warp 1: the bucket of the m-th largest key in this (first) histogram -> its lower edge
-            const int l = threadIdx.x - 32;
-            uint32_t c[8];
-            uint32_t local = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                c[j] = hist[255 - (l * 8 + j)];
-                local += c[j];
-            }
-            uint32_t incl = local;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
-                if (l >= off) incl += v;
-            }
-            uint32_t above = incl - local;
-            if (above < static_cast<uint32_t>(m) && incl >= static_cast<uint32_t>(m)) {
+        if (first_pass && m > 0) {
+            // By-product for the tau exchange: the bucket of the m-th largest key in this (first) histogram, refined once by a
+            // second histogram over that bucket's keys -> a key that at least m keys reach, 16 bits below the first differing
+            // bit (8 bits alone left the bound ~5 % low: twice the candidates per round).  Reuses `hist` after warp 0 has walked
+            // the first histogram for the main selection (whose result sits in bcast[], untouched here).
+            __shared__ uint64_t m_state[2];           // {digit of the m-th key's bucket, keys still needed inside it}
+            auto walk = [&](int need) {               // warp 1: bucket holding the need-th largest of the current histogram
+                const int l = threadIdx.x - 32;
+                uint32_t c[8];
+                uint32_t local = 0;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    if (above + c[j] >= static_cast<uint32_t>(m)) {
-                        *m_lower = prefix | (static_cast<uint64_t>(255 - (l * 8 + j)) << lo);
-                        break;
-                    }
-                    above += c[j];
+                    c[j] = hist[255 - (l * 8 + j)];
+                    local += c[j];
                 }
+                uint32_t incl = local;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+                    if (l >= off) incl += v;
+                }
+                uint32_t above = incl - local;
+                if (above < static_cast<uint32_t>(need) && incl >= static_cast<uint32_t>(need)) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (above + c[j] >= static_cast<uint32_t>(need)) {
+                            m_state[0] = static_cast<uint64_t>(255 - (l * 8 + j));
+                            m_state[1] = static_cast<uint64_t>(need - above);
+                            break;
+                        }
+                        above += c[j];
+                    }
+                }
+            };
+            if (threadIdx.x >= 32 && threadIdx.x < 64) walk(m);
+            __syncthreads();
+            uint64_t m_prefix = prefix | (m_state[0] << lo);
+            const int m_need = static_cast<int>(m_state[1]);
+            if (lo > 0) {                             // second level: the next (up to) 8 bits inside that bucket
+                const uint64_t m_mask = mask | (static_cast<uint64_t>(dmask) << lo);
+                const int hi2 = lo - 1, lo2 = max(0, hi2 - 7);
+                const uint32_t dmask2 = (1u << (hi2 - lo2 + 1)) - 1u;
+                __syncthreads();
+                for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+                __syncthreads();
+                for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                    const uint64_t key = keys[i];
+                    if ((key & m_mask) == m_prefix) atomicAdd(&hist[static_cast<uint32_t>(key >> lo2) & dmask2], 1u);
+                }
+                __syncthreads();
+                if (threadIdx.x >= 32 && threadIdx.x < 64) walk(m_need);
+                __syncthreads();
+                m_prefix |= m_state[0] << lo2;
             }
+            if (threadIdx.x == 0) *m_lower = m_prefix;
         }
         __syncthreads();
         if (first_pass && first_pass_only) return 0;     // the caller only wanted the by-product (block-uniform)

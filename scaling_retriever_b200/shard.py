@@ -129,8 +129,8 @@ class TauExchange:
     vector (28 KB, NCCL over NVLink, enqueued on the search's stream by the hook below — no host synchronisation) gives a
     bound that at least k documents of the whole corpus reach, and every shard continues with it.  The result is unchanged
     (exactly the global top-k after the merge).  Because the bound follows the documents ALL shards have seen, every shard may
-    take larger steps — the docs scored grow 2G + 1 times per round instead of 4 times — for the same ~2-3 k candidates per
-    shard and round: 3 rounds instead of 5 on a 1/8 shard of 8.8 M docs.
+    take larger steps — the docs scored grow max(4, G + 1) times per round instead of 4 times — without more candidates per
+    shard and round: 4 rounds instead of 5 on a 1/8 shard of 8.8 M docs.
     `kind`: "sparse" or "dense" (their round schedules differ); `n_docs_total` sizes the LARGEST shard, which fixes how many
     all-reduces every shard takes part in."""
 

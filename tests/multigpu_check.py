@@ -48,7 +48,7 @@ def main():
 
     # ---- sparse: tau exchange between the rounds (shard.TauExchange), shards with DIFFERENT round counts --------------------
     from scaling_retriever_b200 import _lib
-    growth = _lib.load().b200ret_exchange_growth(world)        # docs scored grow 2G + 1 times per round with the exchange
+    growth = _lib.load().b200ret_exchange_growth(world)        # docs scored grow max(4, G + 1) times per round with the exchange
     bd = ops.block_docs()
     n2 = world * 2 * growth * bd + 1  # ranks 0..G-2: 2g blocks + 1 doc (3 rounds); last rank: 2g blocks (2 rounds + 1 extra exchange)
     rows2, cols2, vals2 = synth.gen_sparse_docs(n2, n_terms=n_terms, mean_nnz=20, seed=15, device=dev)
@@ -68,6 +68,20 @@ def main():
             assert bool((c <= plain[2]).all())
             s, i, c = shard.merge_shards(s, i, kk, n_docs_total=n2)
             assert torch.equal(i, r_i) and torch.equal(c, r_c) and torch.equal(s.view(torch.int32), r_s.view(torch.int32)), ("tau exchange", kk)
+    # forced list overflow (test hook: absurd growth) -> the middle tier re-runs those queries with the shard's own bounds
+    os.environ["B200RET_TEST_EXCHANGE_GROWTH"] = "100000"
+    ex = shard.TauExchange("sparse", n2, dev)
+    assert ex.growth == 100000 and ex.n_exchanges == 1
+    ops.profile_enable(True)
+    ops.profile_read(ops.PROF_SPARSE_SCORE)
+    s, i, c = ops.sparse_search(part2, q_off, q_t, q_w, 1000, 0.0, doc_id_base=lo2, exchange=ex)
+    _, launches_forced, _ = ops.profile_read(ops.PROF_SPARSE_SCORE)
+    ops.profile_enable(False)
+    del os.environ["B200RET_TEST_EXCHANGE_GROWTH"]
+    s, i, c = shard.merge_shards(s, i, 1000, n_docs_total=n2)
+    r_s, r_i, r_c = ops.sparse_search(full2, q_off, q_t, q_w, 1000, 0.0)
+    assert torch.equal(i, r_i) and torch.equal(c, r_c) and torch.equal(s.view(torch.int32), r_s.view(torch.int32)), "overflow middle tier"
+    assert launches_forced > 2, launches_forced          # 2 rounds of the forced schedule + the re-run's rounds
     del full2, part2, rows2, cols2, vals2
 
     # ---- sparse: class API (SparseRetrieval shards by itself under a process group) ------------------------------------
