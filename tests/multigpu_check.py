@@ -21,6 +21,63 @@ from scaling_retriever_b200.indexer import DenseFlatIndexer, SparseRetrieval  # 
 from scaling_retriever_b200.inverted_index import IndexDictOfArray  # noqa: E402
 
 
+def check_overflow_tiers(rank, world, dev):
+    """Candidate-list overflow of a sharded search WITH the tau exchange (forced by the B200RET_TEST_EXCHANGE_GROWTH hook: the
+    second round covers the rest of the shard), on data whose scores rise with the doc id so that every later document passes tau:
+
+    A. "hot" docs (term 0) thinly spread: the plain geometric schedule holds them -> the middle tier (the shard's own bounds, no
+       collectives) finishes the job: 2 forced rounds + 3 plain rounds of the score kernel;
+    B. every doc matches (term 51) -> the middle tier overflows too and the fixed-size safe schedule runs: + 16 rounds.
+    Equal scores sit in different shards (the pattern repeats per shard), so the exchange's strict bound is exercised as well."""
+    from scaling_retriever_b200 import _lib
+    k, bd, round0 = 1000, ops.block_docs(), 2
+    room = max(round0 * bd, 5 * k)                       # candidate capacity = k + room (sparse_search.cu search_cap)
+    n_hot = int(0.7 * room)                              # per plain round: fits; both together: overflow
+    n_shard, n_terms = 32 * bd, 64                       # plain schedule: blocks [0,2) [2,8) [8,32)
+    j = torch.arange(n_shard, device=dev)
+    hot = torch.cat([2 * bd + (torch.arange(n_hot, device=dev) * (6 * bd)) // n_hot,
+                     8 * bd + (torch.arange(n_hot, device=dev) * (24 * bd)) // n_hot])
+    is_hot = torch.zeros(n_shard, dtype=torch.bool, device=dev)
+    is_hot[hot] = True
+    cold = j[~is_hot]
+    l_rows = torch.cat([hot, cold, j])
+    l_cols = torch.cat([torch.zeros_like(hot), 1 + cold % 50, torch.full_like(j, 51)])
+    l_vals = torch.cat([1.0 + torch.arange(hot.numel(), device=dev) * 1e-4, torch.full((cold.numel(),), 0.5, device=dev),
+                        1.0 + j * 1e-5]).float()
+    g_rows = torch.cat([l_rows + g * n_shard for g in range(world)]).to(torch.int32)
+    full = ops.SparseDeviceIndex.from_coo(g_rows, l_cols.repeat(world).to(torch.int32), l_vals.repeat(world), n_terms, world * n_shard)
+    part = ops.SparseDeviceIndex.from_coo(l_rows.to(torch.int32), l_cols.to(torch.int32), l_vals, n_terms, n_shard)
+    lo = rank * n_shard
+    assert shard.ShardPlan(world * n_shard, world).bounds(rank) == (lo, lo + n_shard)
+
+    nq = 48
+    fill = torch.sort(1 + (torch.arange(nq, device=dev)[:, None] * 3 + torch.arange(3, device=dev)[None, :]) % 50, dim=1).values
+    qa_t = torch.cat([torch.zeros(nq, 1, dtype=torch.int64, device=dev), fill], dim=1).reshape(-1).to(torch.int32)
+    qa_w = torch.cat([1.0 + 0.01 * torch.arange(nq, device=dev)[:, None], torch.full((nq, 3), 0.5, device=dev)], dim=1).reshape(-1).float()
+    qa_off = (torch.arange(nq + 1, device=dev) * 4).to(torch.int32)
+    qb_t = torch.full((nq,), 51, dtype=torch.int32, device=dev)
+    qb_w = (1.0 + 0.01 * torch.arange(nq, device=dev)).float()
+    qb_off = torch.arange(nq + 1, device=dev).to(torch.int32)
+
+    os.environ["B200RET_TEST_EXCHANGE_GROWTH"] = "100000"
+    try:
+        assert _lib.load().b200ret_exchange_growth(world) == 100000
+        ex = shard.TauExchange("sparse", world * n_shard, dev)
+        assert ex.growth == 100000 and ex.n_exchanges == 1
+        for name, (off, t, w), want_launches in (("middle tier", (qa_off, qa_t, qa_w), 2 + 3), ("safe tier", (qb_off, qb_t, qb_w), 2 + 3 + 16)):
+            r_s, r_i, r_c = ops.sparse_search(full, off, t, w, k, 0.0)
+            ops.profile_enable(True)
+            ops.profile_read(ops.PROF_SPARSE_SCORE)
+            s, i, c = ops.sparse_search(part, off, t, w, k, 0.0, doc_id_base=lo, exchange=ex)
+            _, launches, _ = ops.profile_read(ops.PROF_SPARSE_SCORE)
+            ops.profile_enable(False)
+            assert launches == want_launches, (name, launches)
+            s, i, c = shard.merge_shards(s, i, k, n_docs_total=world * n_shard)
+            assert torch.equal(i, r_i) and torch.equal(c, r_c) and torch.equal(s.view(torch.int32), r_s.view(torch.int32)), name
+    finally:
+        del os.environ["B200RET_TEST_EXCHANGE_GROWTH"]
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -68,21 +125,8 @@ def main():
             assert bool((c <= plain[2]).all())
             s, i, c = shard.merge_shards(s, i, kk, n_docs_total=n2)
             assert torch.equal(i, r_i) and torch.equal(c, r_c) and torch.equal(s.view(torch.int32), r_s.view(torch.int32)), ("tau exchange", kk)
-    # forced list overflow (test hook: absurd growth) -> the middle tier re-runs those queries with the shard's own bounds
-    os.environ["B200RET_TEST_EXCHANGE_GROWTH"] = "100000"
-    ex = shard.TauExchange("sparse", n2, dev)
-    assert ex.growth == 100000 and ex.n_exchanges == 1
-    ops.profile_enable(True)
-    ops.profile_read(ops.PROF_SPARSE_SCORE)
-    s, i, c = ops.sparse_search(part2, q_off, q_t, q_w, 1000, 0.0, doc_id_base=lo2, exchange=ex)
-    _, launches_forced, _ = ops.profile_read(ops.PROF_SPARSE_SCORE)
-    ops.profile_enable(False)
-    del os.environ["B200RET_TEST_EXCHANGE_GROWTH"]
-    s, i, c = shard.merge_shards(s, i, 1000, n_docs_total=n2)
-    r_s, r_i, r_c = ops.sparse_search(full2, q_off, q_t, q_w, 1000, 0.0)
-    assert torch.equal(i, r_i) and torch.equal(c, r_c) and torch.equal(s.view(torch.int32), r_s.view(torch.int32)), "overflow middle tier"
-    assert launches_forced > 2, launches_forced          # 2 rounds of the forced schedule + the re-run's rounds
     del full2, part2, rows2, cols2, vals2
+    check_overflow_tiers(rank, world, dev)
 
     # ---- sparse: class API (SparseRetrieval shards by itself under a process group) ------------------------------------
     index = IndexDictOfArray(index_path=None, dim_voc=n_terms, device=dev)
