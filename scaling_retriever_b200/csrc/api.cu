@@ -1,6 +1,8 @@
 // Library-level pieces of the C ABI: version, error text, device facts.
 #include <stdarg.h>
 
+#include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -34,9 +36,10 @@ int sm_count() {
 
 // ---- launch accounting + per-kernel CUDA-event timing (bench.py's roofline leg) -------------------------------
 namespace {
-struct ProfileState {
-    bool enabled = false;
-    long long launches = 0;
+struct ProfileState {          // searches may run on several host threads (one per shard / stream): counters are atomic,
+    std::atomic<bool> enabled{false};      // the event lists are guarded by `lock` (only touched while profiling is on)
+    std::atomic<long long> launches{0};
+    std::mutex lock;
     std::vector<cudaEvent_t> pool;                 // recycled events
     std::vector<cudaEvent_t> begin[PROF_KINDS], end[PROF_KINDS];
 };
@@ -57,6 +60,7 @@ void count_launches(int n) { g_prof.launches += n; }
 
 void prof_begin(int kind, cudaStream_t stream) {
     if (!g_prof.enabled) return;
+    std::lock_guard<std::mutex> guard(g_prof.lock);
     cudaEvent_t e = take_event();
     cudaEventRecord(e, stream);
     g_prof.begin[kind].push_back(e);
@@ -64,6 +68,7 @@ void prof_begin(int kind, cudaStream_t stream) {
 
 void prof_end(int kind, cudaStream_t stream) {
     if (!g_prof.enabled) return;
+    std::lock_guard<std::mutex> guard(g_prof.lock);
     cudaEvent_t e = take_event();
     cudaEventRecord(e, stream);
     g_prof.end[kind].push_back(e);
@@ -80,6 +85,7 @@ extern "C" int b200ret_profile_read(int kind, double* total_ms, int64_t* timed_l
     using namespace b200ret;
     B200RET_REQUIRE(kind >= 0 && kind < PROF_KINDS, "profile_read: bad kind %d", kind);
     B200RET_CUDA_CHECK(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> guard(g_prof.lock);
     double ms = 0.0;
     const size_t n = g_prof.end[kind].size();
     for (size_t i = 0; i < n; ++i) {
@@ -94,8 +100,7 @@ extern "C" int b200ret_profile_read(int kind, double* total_ms, int64_t* timed_l
     if (total_ms) *total_ms = ms;
     if (timed_launches) *timed_launches = static_cast<int64_t>(n);
     if (all_launches) {
-        *all_launches = g_prof.launches;
-        g_prof.launches = 0;
+        *all_launches = g_prof.launches.exchange(0);
     }
     return B200RET_OK;
 }

@@ -155,6 +155,7 @@ int launch_select(bool final, const CandBuffers& b, int32_t cap, int32_t k, int3
         const int max_smem = 200 * 1024;
         B200RET_CUDA_CHECK(cudaFuncSetAttribute(select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         B200RET_CUDA_CHECK(cudaFuncSetAttribute(select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        attrs_set.mark();
     }
     if (smem > 200 * 1024) {
         set_err("select: candidate capacity %d needs %zu bytes of shared memory", cap, smem);

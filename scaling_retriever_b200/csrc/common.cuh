@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "../../include/b200ret.h"
 
 namespace b200ret {
@@ -51,15 +53,22 @@ struct Workspace {
 
 int sm_count();
 
-// One-time per-device setup (kernel attributes are per context): `if (once.first()) cudaFuncSetAttribute(...)`.
+// One-time per-device setup (kernel attributes are per context): `if (once.first()) { cudaFuncSetAttribute(...); once.mark(); }`.
 struct PerDeviceOnce {
-    bool done[64] = {};
-    bool first() {
+    std::atomic<bool> done[64] = {};
+    static int device() {
         int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
-        if (done[dev]) return false;
-        done[dev] = true;
-        return true;
+        return (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) ? dev : -1;
+    }
+    // true until the setup has COMPLETED on this device: host threads racing through the first call all do the (idempotent)
+    // setup instead of launching before another thread has finished it
+    bool first() const {
+        const int dev = device();
+        return dev < 0 || !done[dev].load(std::memory_order_acquire);
+    }
+    void mark() {
+        const int dev = device();
+        if (dev >= 0) done[dev].store(true, std::memory_order_release);
     }
 };
 

@@ -503,6 +503,7 @@ extern "C" int b200ret_csr_build(const int32_t* rows, const int32_t* cols, const
     if (attr_set.first()) {
         B200RET_CUDA_CHECK(cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 static_cast<int>(SORT_SCATTER_SMEM)));
+        attr_set.mark();
     }
     const PassPlan plan = make_plan(n_terms, n_docs, sort_docs);
     const int32_t* src_row = rows;
@@ -578,6 +579,7 @@ static int sparse_layout_impl(int fmt, const uint32_t* table, const int32_t* doc
     if (attr_set.first()) {
         B200RET_CUDA_CHECK(cudaFuncSetAttribute(posting_layout_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         B200RET_CUDA_CHECK(cudaFuncSetAttribute(posting_layout_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        attr_set.mark();
     }
     // Two launches: the shared memory of a warp is sized for the longest slice it may meet, and almost all slices are
     // short — sizing every warp for block_docs postings left 4 warps per SM and made the layout latency-bound (0.3 s).

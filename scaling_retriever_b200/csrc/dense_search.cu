@@ -433,6 +433,7 @@ static int dense_search_impl(const void* corpus_bf16, const void* queries_bf16, 
     if (attr_set.first()) {
         B200RET_CUDA_CHECK(cudaFuncSetAttribute(dense_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 static_cast<int>(D_SMEM_BYTES)));
+        attr_set.mark();
     }
     const int grid = (sm_count() / 2) * 2;   // whole pairs
 

@@ -200,6 +200,7 @@ extern "C" int b200ret_merge_topk(const float* in_scores, const int64_t* in_ids,
     if (attr_set.first()) {
         B200RET_CUDA_CHECK(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (MERGE_MAX_CANDIDATES + B200RET_MAX_K) * (int)sizeof(uint64_t)));
+        attr_set.mark();
     }
     merge_topk_kernel<<<n_queries, MERGE_THREADS, smem, stream>>>(in_scores, in_ids, n_shards, n_queries, k, out_scores,
                                                                   out_ids, out_counts);
@@ -250,6 +251,7 @@ extern "C" int b200ret_merge_keys(const uint64_t* in_keys, int32_t n_shards, int
     if (attr_set.first()) {
         B200RET_CUDA_CHECK(cudaFuncSetAttribute(merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (MERGE_MAX_CANDIDATES + B200RET_MAX_K) * (int)sizeof(uint64_t)));
+        attr_set.mark();
     }
     merge_keys_kernel<<<n_queries, MERGE_THREADS, smem, stream>>>(in_keys, n_shards, n_queries, k, out_keys);
     count_launches(1);

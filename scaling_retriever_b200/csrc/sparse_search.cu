@@ -698,6 +698,7 @@ static int launch_score(const ScoreParams& sp, cudaStream_t stream) {
                                                 static_cast<int>(SCORE_SMEM)));
         B200RET_CUDA_CHECK(cudaFuncSetAttribute(sparse_score_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 static_cast<int>(SCORE_SMEM)));
+        attr_set.mark();
     }
     // The item counter is 32 bits wide (claims run past the end by a few per warp): cut the block range so that one
     // launch hands out < 2^31 (query, block) items.

@@ -101,6 +101,7 @@ static int launch_term(TermParams r, int32_t n_vocab, cudaStream_t stream) {
     if (attr_set.first()) {
         B200RET_CUDA_CHECK(cudaFuncSetAttribute(term_gather_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 T_MAX_SMEM_VOCAB * static_cast<int>(sizeof(float))));
+        attr_set.mark();
     }
     // few queries: split the doc range so that every SM has work; many queries: one CTA keeps one query's table resident
     const int sms = sm_count();

@@ -15,63 +15,40 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from scaling_retriever_b200 import ops, shard, synth  # noqa: E402
 from scaling_retriever_b200.indexer import DenseFlatIndexer, SparseRetrieval  # noqa: E402
 from scaling_retriever_b200.inverted_index import IndexDictOfArray  # noqa: E402
+import sharded_helpers as sh  # noqa: E402
 
 
 def check_overflow_tiers(rank, world, dev):
     """Candidate-list overflow of a sharded search WITH the tau exchange (forced by the B200RET_TEST_EXCHANGE_GROWTH hook: the
-    second round covers the rest of the shard), on data whose scores rise with the doc id so that every later document passes tau:
-
-    A. "hot" docs (term 0) thinly spread: the plain geometric schedule holds them -> the middle tier (the shard's own bounds, no
-       collectives) finishes the job: 2 forced rounds + 3 plain rounds of the score kernel;
-    B. every doc matches (term 51) -> the middle tier overflows too and the fixed-size safe schedule runs: + 16 rounds.
-    Equal scores sit in different shards (the pattern repeats per shard), so the exchange's strict bound is exercised as well."""
+    second round covers the rest of the shard) on shards whose scores rise with the doc id (sharded_helpers.rising_score_shard):
+    the middle tier (the shard's own bounds, no collectives) finishes query set A, set B needs the safe schedule as well.  The
+    pattern repeats per shard, so equal scores sit in different shards and the exchange's strict bound is exercised too."""
     from scaling_retriever_b200 import _lib
-    k, bd, round0 = 1000, ops.block_docs(), 2
-    room = max(round0 * bd, 5 * k)                       # candidate capacity = k + room (sparse_search.cu search_cap)
-    n_hot = int(0.7 * room)                              # per plain round: fits; both together: overflow
-    n_shard, n_terms = 32 * bd, 64                       # plain schedule: blocks [0,2) [2,8) [8,32)
-    j = torch.arange(n_shard, device=dev)
-    hot = torch.cat([2 * bd + (torch.arange(n_hot, device=dev) * (6 * bd)) // n_hot,
-                     8 * bd + (torch.arange(n_hot, device=dev) * (24 * bd)) // n_hot])
-    is_hot = torch.zeros(n_shard, dtype=torch.bool, device=dev)
-    is_hot[hot] = True
-    cold = j[~is_hot]
-    l_rows = torch.cat([hot, cold, j])
-    l_cols = torch.cat([torch.zeros_like(hot), 1 + cold % 50, torch.full_like(j, 51)])
-    l_vals = torch.cat([1.0 + torch.arange(hot.numel(), device=dev) * 1e-4, torch.full((cold.numel(),), 0.5, device=dev),
-                        1.0 + j * 1e-5]).float()
-    g_rows = torch.cat([l_rows + g * n_shard for g in range(world)]).to(torch.int32)
-    full = ops.SparseDeviceIndex.from_coo(g_rows, l_cols.repeat(world).to(torch.int32), l_vals.repeat(world), n_terms, world * n_shard)
-    part = ops.SparseDeviceIndex.from_coo(l_rows.to(torch.int32), l_cols.to(torch.int32), l_vals, n_terms, n_shard)
+    k = 1000
+    (l_rows, l_cols, l_vals), n_shard, n_terms, qa, qb = sh.rising_score_shard(dev, k)
+    g_rows = torch.cat([l_rows + g * n_shard for g in range(world)])
+    full = ops.SparseDeviceIndex.from_coo(g_rows, l_cols.repeat(world), l_vals.repeat(world), n_terms, world * n_shard)
+    part = ops.SparseDeviceIndex.from_coo(l_rows, l_cols, l_vals, n_terms, n_shard)
     lo = rank * n_shard
     assert shard.ShardPlan(world * n_shard, world).bounds(rank) == (lo, lo + n_shard)
-
-    nq = 48
-    fill = torch.sort(1 + (torch.arange(nq, device=dev)[:, None] * 3 + torch.arange(3, device=dev)[None, :]) % 50, dim=1).values
-    qa_t = torch.cat([torch.zeros(nq, 1, dtype=torch.int64, device=dev), fill], dim=1).reshape(-1).to(torch.int32)
-    qa_w = torch.cat([1.0 + 0.01 * torch.arange(nq, device=dev)[:, None], torch.full((nq, 3), 0.5, device=dev)], dim=1).reshape(-1).float()
-    qa_off = (torch.arange(nq + 1, device=dev) * 4).to(torch.int32)
-    qb_t = torch.full((nq,), 51, dtype=torch.int32, device=dev)
-    qb_w = (1.0 + 0.01 * torch.arange(nq, device=dev)).float()
-    qb_off = torch.arange(nq + 1, device=dev).to(torch.int32)
-
     os.environ["B200RET_TEST_EXCHANGE_GROWTH"] = "100000"
     try:
         assert _lib.load().b200ret_exchange_growth(world) == 100000
         ex = shard.TauExchange("sparse", world * n_shard, dev)
         assert ex.growth == 100000 and ex.n_exchanges == 1
-        for name, (off, t, w), want_launches in (("middle tier", (qa_off, qa_t, qa_w), 2 + 3), ("safe tier", (qb_off, qb_t, qb_w), 2 + 3 + 16)):
+        for name, (off, t, w), want in (("middle tier", qa, sh.LAUNCHES_MIDDLE_TIER), ("safe tier", qb, sh.LAUNCHES_SAFE_TIER)):
             r_s, r_i, r_c = ops.sparse_search(full, off, t, w, k, 0.0)
             ops.profile_enable(True)
             ops.profile_read(ops.PROF_SPARSE_SCORE)
             s, i, c = ops.sparse_search(part, off, t, w, k, 0.0, doc_id_base=lo, exchange=ex)
             _, launches, _ = ops.profile_read(ops.PROF_SPARSE_SCORE)
             ops.profile_enable(False)
-            assert launches == want_launches, (name, launches)
+            assert launches == want, (name, launches)
             s, i, c = shard.merge_shards(s, i, k, n_docs_total=world * n_shard)
             assert torch.equal(i, r_i) and torch.equal(c, r_c) and torch.equal(s.view(torch.int32), r_s.view(torch.int32)), name
     finally:
