@@ -186,9 +186,9 @@ int b200ret_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, void* strea
  * A doc-range sharded search runs the rounds of (2)/(3) on every shard.  Alone, a shard can only raise its bound tau[q] to
  * ITS k-th best score, so every shard emits and selects as many candidates per round as a whole corpus would.  With the
  * exchange, after every round each shard also publishes aux[q] = a score that at least ceil(k / n_shards) of its candidates so
- * far reach (read off the first histogram of the round's radix selection; -inf if it has fewer candidates); `hook` — provided
- * by the host side, which owns the communicator — all-reduces aux with MIN over
- * the shards on the search's stream, and tau[q] is raised to just below that minimum: every shard holds at least
+ * far reach (a by-product of the round's radix selection, two 8-bit histogram levels deep; -inf if it has fewer
+ * candidates); `hook` — provided by the host side, which owns the communicator — all-reduces aux with MIN over the
+ * shards on the search's stream, and tau[q] is raised to just below that minimum: every shard holds at least
  * ceil(k / n_shards) documents at or above it, so at least k documents of the corpus do, and a document scoring strictly
  * below it cannot be in the global top-k.  Results are exactly those of the plain entry points after the merge.
  * `hook(user)` must ENQUEUE the all-reduce (no host synchronisation) and return 0; it is called exactly `n_exchanges` times

@@ -8,7 +8,9 @@
 // The docs scored grow ROUND_GROWTH x per round, so about (ROUND_GROWTH - 1) * k new candidates per query and round
 // survive tau on exchangeable data; the capacity is k + max(first-round docs, (ROUND_GROWTH + 1) * k), i.e. at least two k
 // of head-room over that expectation for every k up to B200RET_MAX_K.  A list that overflows anyway (adversarial doc
-// order) is flagged and the query is re-run with fixed rounds of the first-round size, which cannot overflow.
+// order) is flagged and the query is re-run with fixed rounds of the first-round size, which cannot overflow.  A sharded
+// search with the tau exchange (b200ret_round_exchange) grows by exchange_growth(n_shards) per round instead and has a middle
+// tier before that: overflowed queries are first re-run with the shard's own bounds and the plain schedule (run_search).
 #pragma once
 #include <algorithm>
 #include <cstdlib>

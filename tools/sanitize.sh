@@ -13,5 +13,10 @@ echo "memcheck exit: ${PIPESTATUS[0]}" | tee -a $O
 echo "== racecheck ==" | tee -a $O
 timeout 1500 compute-sanitizer --tool racecheck --racecheck-report all --error-exitcode 9 python -m pytest tests/test_sparse_gpu.py \
   tests/test_merge_gpu.py tests/test_term_gpu.py tests/test_sharded_gpu.py -m gpu -q -x \
-  -k "ragged or golden or merge or csr_build_matches_oracle or posting_layout or fp16 or term_scores_and_search or threads" 2>&1 | tail -4 | tee -a $O
-echo "racecheck exit: ${PIPESTATUS[0]}" | tee -a $O
+  -k "ragged or golden or merge or csr_build_matches_oracle or posting_layout or fp16 or term_scores_and_search or (threads and sparse)" \
+  > gpurun_out/r02_racecheck_full.log 2>&1
+rc=$?
+grep -m 12 -A6 "Race reported\|hazard detected" gpurun_out/r02_racecheck_full.log | head -60 | tee -a $O    # first hazards, if any
+tail -4 gpurun_out/r02_racecheck_full.log | tee -a $O
+echo "racecheck exit: $rc" | tee -a $O
+exit 0
